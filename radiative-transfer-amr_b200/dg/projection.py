@@ -1,0 +1,159 @@
+"""Nodal fields on an hp mesh.
+
+Drop-in for the reference's ``dg.projection`` (``class_Projection.py:17-98``,
+``to_vector.py:11-44``, ``from_vector.py:11-40``, ``to_file.py:10-19``,
+``from_file.py:14-21``, ``push_pull.py:10-26``).  A ``Projection`` stores one
+``vals[nx, ny, nth]`` array per cell; ``to_vector``/``from_vector`` fix the
+global vector layout used at the solver boundary.
+"""
+from __future__ import annotations
+
+import copy
+
+import numpy as np
+
+from .mesh import Mesh, from_file as mesh_from_file
+from .quadrature import quad_xyth
+
+
+def push_forward(x0: float, xf: float, nodes: np.ndarray) -> np.ndarray:
+    """[-1, 1] -> [x0, xf] (``push_pull.py:10-17``)."""
+    return x0 + (xf - x0) / 2.0 * (nodes + 1.0)
+
+
+def pull_back(x0: float, xf: float, nodes: np.ndarray) -> np.ndarray:
+    """[x0, xf] -> [-1, 1] (``push_pull.py:19-26``)."""
+    return -1.0 + 2.0 / (xf - x0) * (nodes - x0)
+
+
+class Projection_Cell:
+    def __init__(self, cell, vals: np.ndarray):
+        self.pos = cell.pos[:]
+        self.idx = cell.idx
+        self.lv = cell.lv
+        self.key = cell.key
+        self.is_lf = cell.is_lf
+        self.ndofs = cell.ndofs[:]
+        self.quadrant = cell.quadrant
+        self.nhbr_keys = cell.nhbr_keys
+        self.vals = vals
+
+    def __eq__(self, other):
+        meta = (self.pos, self.idx, self.lv, self.key, self.is_lf, self.ndofs,
+                self.quadrant, self.nhbr_keys)
+        ometa = (other.pos, other.idx, other.lv, other.key, other.is_lf, other.ndofs,
+                 other.quadrant, other.nhbr_keys)
+        return meta == ometa and bool(np.min(self.vals == other.vals))
+
+
+class Projection_Column:
+    def __init__(self, col, projection_cells: dict):
+        self.pos = col.pos[:]
+        self.idx = col.idx[:]
+        self.lv = col.lv
+        self.key = col.key
+        self.is_lf = col.is_lf
+        self.ndofs = col.ndofs[:]
+        self.nhbr_keys = col.nhbr_keys[:]
+        self.cells = projection_cells
+
+    def __eq__(self, other):
+        meta = (self.pos, self.idx, self.lv, self.key, self.is_lf, self.ndofs,
+                self.nhbr_keys)
+        ometa = (other.pos, other.idx, other.lv, other.key, other.is_lf, other.ndofs,
+                 other.nhbr_keys)
+        return meta == ometa and self.cells == other.cells
+
+
+class Projection:
+    """Nodal interpolant of ``func(x, y, th)`` (or zero) on a private copy of
+    ``mesh``.  ``func`` may accept scalars only; it is called node by node like
+    the reference does, unless ``vectorized=True`` is passed, in which case it
+    is called once per cell with broadcastable arrays."""
+
+    def __init__(self, mesh: Mesh, func=None, vectorized: bool = False):
+        self.mesh = copy.deepcopy(mesh)
+        has_th = mesh.has_th
+        cols = {}
+        for col_key, col in sorted(self.mesh.cols.items()):
+            assert col.is_lf
+            x0, y0, x1, y1 = col.pos
+            nx, ny = col.ndofs
+            xb, _, yb, _, _, _ = quad_xyth(nnodes_x=nx, nnodes_y=ny)
+            xf = push_forward(x0, x1, xb)
+            yf = push_forward(y0, y1, yb)
+            cells = {}
+            for cell_key, cell in sorted(col.cells.items()):
+                assert cell.is_lf
+                if has_th:
+                    nth = cell.ndofs[0]
+                    _, _, _, _, thb, _ = quad_xyth(nnodes_th=nth)
+                    thf = push_forward(cell.pos[0], cell.pos[1], thb)
+                else:
+                    nth = 1
+                    thf = np.zeros([1])
+                vals = np.zeros([nx, ny, nth])
+                if func is not None:
+                    if vectorized:
+                        X = xf.reshape(nx, 1, 1)
+                        Y = yf.reshape(1, ny, 1)
+                        T = thf.reshape(1, 1, nth)
+                        out = func(X, Y, T) if has_th else func(X, Y)
+                        vals[:, :, :] = np.broadcast_to(out, vals.shape)
+                    else:
+                        for ii in range(nx):
+                            for jj in range(ny):
+                                for aa in range(nth):
+                                    if has_th:
+                                        vals[ii, jj, aa] = func(xf[ii], yf[jj], thf[aa])
+                                    else:
+                                        vals[ii, jj, aa] = func(xf[ii], yf[jj])
+                cells[cell_key] = Projection_Cell(cell, vals)
+            cols[col_key] = Projection_Column(col, cells)
+        self.cols = cols
+
+    def to_vector(self) -> np.ndarray:
+        """Global vector: sorted columns, sorted cells, C-order of
+        ``vals[i, j, a]`` (``to_vector.py:16-42``)."""
+        parts = []
+        for _, col in sorted(self.cols.items()):
+            for _, cell in sorted(col.cells.items()):
+                parts.append(np.asarray(cell.vals, dtype=np.float64).reshape(-1))
+        return np.concatenate(parts, axis=None)
+
+    def from_vector(self, vec: np.ndarray):
+        """Inverse of :meth:`to_vector` (``from_vector.py:11-40``)."""
+        vec = np.asarray(vec)
+        g = 0
+        for col_key, col in sorted(self.mesh.cols.items()):
+            assert col.is_lf
+            nx, ny = col.ndofs
+            for cell_key, cell in sorted(col.cells.items()):
+                assert cell.is_lf
+                nth = cell.ndofs[0]
+                n = nx * ny * nth
+                self.cols[col_key].cells[cell_key].vals = \
+                    np.array(vec[g:g + n], dtype=np.float64).reshape(nx, ny, nth)
+                g += n
+        return self
+
+    def to_file(self, file_path: str = "projection.npy", **kwargs) -> None:
+        """Raw float64 dump of the global vector (+ mesh JSON), byte-compatible
+        with ``dg/projection/to_file.py:10-19``."""
+        opts = {"write_mesh": True, "mesh_file_path": "mesh.json", **kwargs}
+        if opts["write_mesh"]:
+            self.mesh.to_file(opts["mesh_file_path"])
+        self.to_vector().tofile(file_path)
+
+    def __eq__(self, other):
+        return self.mesh == other.mesh and self.cols == other.cols
+
+
+def from_file(mesh_file_path: str = "mesh.json",
+              projection_file_path: str = "projection.npy") -> Projection:
+    """Read a projection written by ``Projection.to_file``
+    (``dg/projection/from_file.py:14-21``)."""
+    mesh = mesh_from_file(mesh_file_path)
+    proj = Projection(mesh, None)
+    proj.from_vector(np.fromfile(projection_file_path))
+    return proj
