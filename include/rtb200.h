@@ -1,0 +1,239 @@
+/*
+ * rtb200.h -- C ABI of librtb200.so, the B200 (sm_100a) transport-operator
+ * library for hp-adaptive DGSEM radiative transfer (2-D space x 1-D angle).
+ *
+ * The reference (jasonltorchinsky/radiative-transfer-amr) is pure Python and
+ * has no FFI layer: its "operator apply" is PETSc MatMult on the AIJ matrix
+ * A = (BC - IC) + (M - S) assembled by src/rt (solve.py:49-54,68,100).  The
+ * entry points below are what a binding for that path attaches to; each one
+ * names the reference interface it replaces.  INTEGRATION.md shows the ctypes
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes; no torch / C++ types in signatures;
+ *   - every function returns 0 on success and a negative RTB200_E* code on
+ *     failure, never throws or aborts; rtb200_last_error() gives the message;
+ *   - the library never allocates caller-visible memory: vectors and the GMRES
+ *     workspace are device buffers owned by the caller (PyTorch in this repo);
+ *     the context owns only its private copies of the mesh tables;
+ *   - one context per process per GPU, not thread-safe; all work is enqueued on
+ *     the cudaStream_t passed as `void* stream`;
+ *   - solver non-convergence is not an error: it is reported in
+ *     rtb200_gmres_result.reason with PETSc's KSPConvergedReason codes.
+ *
+ * Vector layouts
+ *   "dof order"  : the reference's global vector (dg/projection/to_vector.py:
+ *                  16-42): columns in sorted-key order, cells in sorted-key
+ *                  order, then (i, j, a) with the angular index fastest.
+ *   "slab order" : the library's internal layout: per column one slab
+ *                  [node = i*ny + j][theta], theta running over the column's
+ *                  cells in sorted-key order, row stride padded to an even
+ *                  count; pad entries are zero.  rtb200_to_slab / _from_slab
+ *                  convert.  apply/gmres work on slab-order device vectors of
+ *                  rtb200_flatmesh.n_slab doubles.
+ */
+#ifndef RTB200_H
+#define RTB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTB200_ABI_VERSION 1
+
+/* error codes */
+#define RTB200_OK            0
+#define RTB200_EINVAL       -1   /* bad argument / inconsistent tables     */
+#define RTB200_ECUDA        -2   /* CUDA runtime error (see last_error)    */
+#define RTB200_ESTATE       -3   /* call out of order (e.g. no mesh set)   */
+#define RTB200_EUNSUPPORTED -4   /* size outside the compiled limits       */
+#define RTB200_ENCCL        -5   /* NCCL error                             */
+
+/* operator terms, with the sign they carry in A = (BC - IC) + (M - S)
+ * (reference: src/rt/solve.py:52) */
+#define RTB200_TERM_MASS   1u    /* + M   mass_matrix.py:105-180                    */
+#define RTB200_TERM_SCAT   2u    /* - S   scattering_matrix.py / preconditioner_matrix.py:116-267 */
+#define RTB200_TERM_ICONV  4u    /* - IC  interior_convection_matrix.py:110-250     */
+#define RTB200_TERM_BCONV  8u    /* + BC  boundary_convection_matrix.py:160-540     */
+#define RTB200_TERM_ALL   15u
+
+/* limits of the compiled kernels */
+#define RTB200_MAX_NXY     12    /* max nodes per spatial direction in a column */
+#define RTB200_MAX_NTH     16    /* max angular nodes per cell                   */
+
+typedef struct rtb200_ctx rtb200_ctx;
+
+/*
+ * Flattened hp-mesh layout, built on the host
+ * once per AMR step from the reference's Mesh object
+ * (dg/mesh/class_Mesh.py:12-90) by rt_b200.dg.flatmesh.  All pointers are HOST
+ * pointers; rtb200_set_mesh copies them to the device.
+ *
+ * Column c (position in sorted-key order, restricted to this rank's block):
+ *   nx, ny, angular signature, sizes, slab/dof offsets, boundary faces.
+ * Angular signature s: the ordered list of (cell key, n_theta) of a column;
+ *   columns with equal signatures share every angular table and G.
+ * Face tables are indexed [c*8 + F*2 + slot], F: 0=+x 1=+y 2=-x 3=-y,
+ *   slot 0/1 = first/second neighbour column across the face
+ *   (Column.nhbr_keys[F], counter-clockwise order).
+ */
+typedef struct rtb200_flatmesh {
+    int32_t abi_version;
+    int32_t n_col;              /* columns owned by this rank                    */
+    int32_t n_sig;              /* distinct angular signatures                   */
+    int32_t n_sigcell;          /* total cells over all signatures               */
+    int64_t n_dof;              /* doubles in a dof-order vector (owned columns) */
+    int64_t n_slab;             /* doubles in a slab-order vector                */
+    int64_t n_ghost;            /* doubles in the halo (ghost trace) buffer      */
+
+    /* per column [n_col] */
+    const int32_t* col_nx;
+    const int32_t* col_ny;
+    const int32_t* col_sig;
+    const int32_t* col_bdry;    /* bit F set: face F lies on the domain boundary */
+    const int64_t* col_dof_off; /* first dof-order index                         */
+    const int64_t* col_slab_off;/* first slab-order index (even)                 */
+    const int64_t* col_coef_off;/* first index into coef (2*nx*ny doubles/column)*/
+    const double*  col_dx;
+    const double*  col_dy;
+
+    /* per (column, face, slot) [n_col*8] */
+    const int64_t* face_base;   /* slab index of the neighbour's first face row
+                                   (node j=0, theta 0); >= 0: in x;
+                                   <= -2: -(v+2) indexes the ghost buffer;
+                                   -1: no neighbour in this slot                 */
+    const int32_t* face_rstride;/* doubles between consecutive face nodes there  */
+    const int32_t* face_exy;    /* offset into exy_pool of E[n1][n0] (row j, col q) */
+    const int32_t* face_n1;     /* face nodes of the neighbour column            */
+    const int32_t* face_acpl;   /* offset into acpl_pool                         */
+
+    /* per signature [n_sig] */
+    const int32_t* sig_nt;      /* angular DoFs of a column                      */
+    const int32_t* sig_ntp;     /* row stride (nt rounded up to even)            */
+    const int32_t* sig_ncell;
+    const int32_t* sig_cell0;   /* first entry in the sigcell arrays             */
+    const int64_t* sig_th0;     /* first entry in the per-theta arrays           */
+    const int64_t* sig_g_off;   /* first entry in g_pool ([ntp][ntp], G^T)       */
+
+    /* per signature cell [n_sigcell], sorted-key order inside a signature */
+    const int32_t* cell_nth;
+    const int32_t* cell_thoff;  /* first theta index of the cell in its column   */
+
+    /* per theta, pooled over signatures (ntp entries each, pad entries zero) */
+    int64_t n_theta_pool;
+    const double*  th_wt;       /* (dtheta/2) * w_a                              */
+    const double*  th_ct;       /* th_wt * cos(theta)                            */
+    const double*  th_st;       /* th_wt * sin(theta)                            */
+    const double*  th_wF;       /* [4][n_theta_pool]: th_wt * cos(theta - F pi/2)*/
+    const int32_t* th_cell;     /* cell index inside the signature               */
+    const int32_t* th_bits;     /* bits 0-3: face F is OUTFLOW for the cell's
+                                   quadrant; bits 4-7: face F is INFLOW for the
+                                   mask (get_masks.py:80-110); bits 8-15: index
+                                   of the dof inside its cell                    */
+
+    /* pools */
+    int64_t n_g_pool;     const double*  g_pool;    /* per signature G^T, [theta'][theta] */
+    int64_t n_exy_pool;   const double*  exy_pool;  /* spatial mortars E^x / E^y          */
+    int64_t n_eth_pool;   const double*  eth_pool;  /* (dtheta0/2) * E^theta blocks [a][r]*/
+    int64_t n_acpl_pool;  const int32_t* acpl_pool; /* per (sig0, sig1, F): [ncell0][2][3]
+                                                       = (eth offset, theta' start, n_theta1) */
+
+    /* per n = 0..RTB200_MAX_NXY: LGL weights and S[p][i] = phi_p'(xi_i) w_i */
+    const double*  lgl_w;       /* [(MAX_NXY+1)][MAX_NXY]                        */
+    const double*  lgl_s;       /* [(MAX_NXY+1)][MAX_NXY][MAX_NXY]               */
+
+    /* coefficient samples: per column, mk[node] then ms[node]
+       mk = (dx dy/4) w_i w_j kappa(x_i, y_j),  ms = (dx dy/4) w_i w_j sigma(x_i, y_j) */
+    int64_t n_coef;       const double*  coef;
+
+    /* halo exchange plan (multi-GPU; all zero / NULL on one GPU) */
+    int32_t n_peer;             /* ranks this rank exchanges traces with         */
+    const int32_t* peer_rank;   /* [n_peer]                                      */
+    const int64_t* peer_send0;  /* [n_peer+1] ranges in send_src                 */
+    const int64_t* peer_recv0;  /* [n_peer+1] ranges in the ghost buffer         */
+    int64_t n_send;       const int64_t* send_src;  /* slab index of every double to send */
+} rtb200_flatmesh;
+
+typedef struct rtb200_gmres_params {
+    int32_t restart;        /* Krylov dimension before restart (reference: 50, solve.py:90) */
+    int32_t max_it;         /* reference: 5000 (solve.py:86)                                */
+    double  rtol;           /* reference: consts.EPS = 1e-15                                */
+    double  atol;           /* reference: consts.EPS = 1e-15                                */
+    double  divtol;         /* reference: sqrt(consts.INF)                                  */
+    int32_t orth;           /* 0: classical Gram-Schmidt, refine if needed (DGKS);
+                               1: always two passes; 2: never refine (PETSc default)        */
+    int32_t pc;             /* 0: none; 1: block-Jacobi over (node, column) angular blocks  */
+    int32_t x0_nonzero;     /* reference: 1 (solve.py:97)                                   */
+    int32_t record_history; /* 1: write residual norms to hist                              */
+} rtb200_gmres_params;
+
+typedef struct rtb200_gmres_result {
+    int32_t reason;         /* PETSc code: 2 RTOL, 3 ATOL, -3 ITS, -4 DTOL, -5 BREAKDOWN     */
+    int32_t iterations;
+    double  res_norm;       /* last (preconditioned) residual norm estimate                 */
+    double  res0_norm;      /* initial residual norm                                        */
+    double  b_norm;
+    double  true_res_norm;  /* ||b - A x|| recomputed at exit                               */
+    double  sigma_max;      /* extreme singular values of the Hessenberg matrix, the        */
+    double  sigma_min;      /*   estimate behind KSPComputeExtremeSingularValues            */
+    int64_t n_apply;        /* operator applications performed                              */
+} rtb200_gmres_result;
+
+/* ---- life cycle -------------------------------------------------------- */
+int  rtb200_abi_version(void);
+int  rtb200_create(int device, rtb200_ctx** out);
+void rtb200_destroy(rtb200_ctx* ctx);
+const char* rtb200_last_error(const rtb200_ctx* ctx);
+
+/* ---- element tables (replaces the five calc_col_matrix assemblers:
+ *      preconditioner_matrix.py:116, interior_convection_matrix.py:110,
+ *      boundary_convection_matrix.py:160, mass/scattering_matrix.py) ---- */
+int  rtb200_set_mesh(rtb200_ctx* ctx, const rtb200_flatmesh* mesh);
+/* new kappa/sigma samples on an unchanged mesh (same layout as flatmesh.coef) */
+int  rtb200_set_coeffs(rtb200_ctx* ctx, const double* coef_host, int64_t n_coef);
+
+/* ---- layout conversion (dg/projection/to_vector.py:16-42,
+ *      from_vector.py:11-40 define dof order) --------------------------- */
+int  rtb200_to_slab(rtb200_ctx* ctx, const double* x_dof_dev, double* x_slab_dev, void* stream);
+int  rtb200_from_slab(rtb200_ctx* ctx, const double* x_slab_dev, double* x_dof_dev, void* stream);
+
+/* keep = 1: zero the inflow-boundary entries (x <- mask .* x);
+ * keep = 2: zero the interior entries        (x <- (1 - mask) .* x)
+ * (dg/matrix/get_masks.py:19-129, split_vector.py:15-48) */
+int  rtb200_mask(rtb200_ctx* ctx, double* x_slab_dev, int keep, void* stream);
+
+/* ---- operator apply: y = sum of the selected terms applied to x
+ *      (replaces PETSc MatMult on sys_mat / A_ii / A_ib, solve.py:52-54,68,100).
+ *      interior_only = 1: rows of inflow-boundary DoFs are written as zero
+ *      (A[I, :] x); with x zero on the boundary this is A_ii x, with x zero
+ *      in the interior it is A_ib g.  x and y must not alias. ------------ */
+int  rtb200_apply(rtb200_ctx* ctx, unsigned terms, int interior_only,
+                  const double* x_slab_dev, double* y_slab_dev, void* stream);
+
+/* ---- Krylov solve of A_ii x = b (replaces KSPSolve, solve.py:80-100).
+ *      b, x: slab order, zero on boundary entries and pads.
+ *      work: rtb200_gmres_work_bytes() bytes of device memory.
+ *      hist: host array of max_it+1 doubles or NULL. -------------------- */
+int64_t rtb200_gmres_work_bytes(const rtb200_ctx* ctx, int restart);
+int  rtb200_gmres(rtb200_ctx* ctx, const double* b_dev, double* x_dev,
+                  const rtb200_gmres_params* prm, rtb200_gmres_result* res,
+                  double* hist_host, void* work_dev, int64_t work_bytes, void* stream);
+
+/* ---- multi-GPU: one process per GPU; columns split like the reference's
+ *      np.array_split(sorted keys, size)[rank] (mass_matrix.py:50-51).
+ *      The communicator is created inside the library from an ncclUniqueId
+ *      that rank 0 obtains with rtb200_nccl_unique_id and the host broadcasts
+ *      (torch.distributed in this repo). -------------------------------- */
+int  rtb200_nccl_unique_id(char* id128);                 /* 128-byte buffer */
+int  rtb200_comm_init(rtb200_ctx* ctx, const char* id128, int rank, int nranks);
+int  rtb200_halo_exchange(rtb200_ctx* ctx, const double* x_slab_dev, void* stream);
+
+/* ---- instrumentation -------------------------------------------------- */
+int64_t rtb200_launch_count(const rtb200_ctx* ctx);      /* kernels launched so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTB200_H */

@@ -1,0 +1,91 @@
+// Internal declarations shared by the translation units of librtb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "rtb200.h"
+
+#define RT_MAXN RTB200_MAX_NXY
+
+// Device-side view of rtb200_flatmesh (all pointers are device pointers).
+struct DevMesh {
+    int32_t n_col;
+    int64_t n_dof, n_slab;
+    const int32_t *col_nx, *col_ny, *col_sig, *col_bdry;
+    const int64_t *col_dof_off, *col_slab_off, *col_coef_off;
+    const double *col_dx, *col_dy;
+    const int64_t* face_base;
+    const int32_t *face_rstride, *face_exy, *face_n1, *face_acpl;
+    const int32_t *sig_nt, *sig_ntp, *sig_ncell, *sig_cell0;
+    const int64_t *sig_th0, *sig_g_off;
+    const int32_t *cell_nth, *cell_thoff;
+    int64_t n_theta_pool;
+    const double *th_wt, *th_ct, *th_st, *th_wF;
+    const int32_t *th_cell, *th_bits;
+    const double *g_pool, *exy_pool, *eth_pool;
+    const int32_t* acpl_pool;
+    const double* coef;
+};
+
+// A launch bucket: columns with nx == ny == n (n = 0: anything else).
+struct Bucket {
+    int n = 0;                 // template selector
+    int count = 0;
+    int max_ntp = 0;
+    size_t smem = 0;           // bytes of dynamic shared memory (largest slab)
+    int32_t* cols_dev = nullptr;
+};
+
+struct NcclApi;                // resolved with dlopen in comm.cu
+
+struct rtb200_ctx {
+    int device = 0;
+    std::string err;
+    bool have_mesh = false;
+    DevMesh dm{};
+    std::vector<void*> allocs; // private device allocations (tables)
+    std::vector<Bucket> buckets;
+    double* coef_dev = nullptr;
+    int64_t n_coef = 0;
+    int64_t launches = 0;
+    int sm_count = 148;
+
+    // block-Jacobi preconditioner state (bjacobi.cu)
+    double* pc_inv = nullptr;      // [sum over columns nn * ntp * ntp]
+    int64_t* pc_off = nullptr;     // [n_col]
+    bool pc_ready = false;
+
+    // halo / multi-GPU
+    int rank = 0, nranks = 1;
+    void* nccl_comm = nullptr;
+    NcclApi* nccl = nullptr;
+    int64_t n_ghost = 0, n_send = 0;
+    double* ghost_dev = nullptr;
+    double* send_dev = nullptr;
+    int64_t* send_src_dev = nullptr;
+    std::vector<int32_t> peer_rank;
+    std::vector<int64_t> peer_send0, peer_recv0;
+};
+
+int rt_fail(rtb200_ctx* ctx, int code, const std::string& msg);
+int rt_cuda(rtb200_ctx* ctx, cudaError_t e, const char* what);
+
+#define RT_CUDA(ctx, call)                                        \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) return rt_cuda(ctx, e__, #call);  \
+    } while (0)
+
+// apply.cu
+int rt_launch_apply(rtb200_ctx* ctx, unsigned terms, int interior_only, const double* x,
+                    double* y, cudaStream_t st);
+int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m);
+// comm.cu
+int rt_allreduce_sum(rtb200_ctx* ctx, double* buf_dev, int count, cudaStream_t st);
+void rt_comm_destroy(rtb200_ctx* ctx);
+// bjacobi.cu
+int rt_pc_setup(rtb200_ctx* ctx, cudaStream_t st);
+int rt_pc_apply(rtb200_ctx* ctx, const double* x, double* y, cudaStream_t st);
+void rt_pc_destroy(rtb200_ctx* ctx);

@@ -1,0 +1,267 @@
+"""``Problem``: the reference's RT entry points, running on the B200 library.
+
+Same constructor, method names, argument meaning and return shapes as
+``src/rt/class_Problem.py:11-32`` and ``src/rt/solve.py:21-149``:
+
+    problem = Problem(kappa, sigma, Phi, f, bcs_dirac)
+    [uh_proj, convergence_info, matrix_info] = problem.solve(mesh, ksp_type=..., pc_type=...)
+
+What differs is where the arithmetic happens: no sparse matrix is assembled.
+The operator builders return ``TermOperator`` objects whose ``mult(x, y)`` runs
+the matrix-free CUDA kernels (the reference returns PETSc AIJ matrices), and
+``solve`` runs restarted GMRES on the device.
+
+kappa, sigma are called on broadcastable grids, Phi / f / bcs with scalars or
+broadcastable arrays (scalar fall-back), as in the reference.
+"""
+from __future__ import annotations
+
+from time import perf_counter
+
+import numpy as np
+
+from .. import consts
+from .. import _lib as L
+from ..dg.flatmesh import FlatMesh
+from ..dg.projection import Projection, push_forward, pull_back
+from ..dg.quadrature import quad_xyth, lag_eval
+from .operator import RTOperator
+
+
+def _eval_nodal(fn, X, Y, Th):
+    """fn on the (x, y, theta) tensor grid of one cell; one broadcast call when
+    the callable supports it, scalar calls otherwise (``forcing_vector.py:151``,
+    ``boundary_conditions_vector.py:199-205``)."""
+    nx, ny, nth = X.shape[0], Y.shape[0], Th.shape[0]
+    try:
+        out = np.asarray(fn(X.reshape(nx, 1, 1), Y.reshape(1, ny, 1), Th.reshape(1, 1, nth)),
+                         dtype=np.float64)
+        if out.shape == (nx, ny, nth):
+            return out
+        if out.shape == ():
+            return np.full((nx, ny, nth), float(out))
+    except Exception:
+        pass
+    out = np.zeros((nx, ny, nth))
+    for i in range(nx):
+        for j in range(ny):
+            for a in range(nth):
+                out[i, j, a] = fn(X[i], Y[j], Th[a])
+    return out
+
+
+class TermOperator:
+    """``sign * (selected terms of A)`` with a PETSc-``Mat``-like ``mult``."""
+
+    def __init__(self, op: RTOperator, terms: int, sign: float = 1.0):
+        self.op, self.terms, self.sign = op, terms, sign
+        self.shape = op.shape
+
+    def getSize(self):
+        return self.shape
+
+    def mult(self, x, y=None):
+        out = self.op.mult(x, None, self.terms, False)
+        if self.sign != 1.0:
+            out = out * self.sign
+        if y is not None:
+            if isinstance(y, np.ndarray):
+                y[...] = out
+            else:
+                y.copy_(out)
+            return y
+        return out
+
+    def __matmul__(self, x):
+        return self.mult(x)
+
+
+class Problem:
+    def __init__(self, kappa, sigma, Phi, f, bcs_dirac):
+        self.kappa = kappa
+        self.sigma = sigma
+        self.Phi = Phi
+        self.f = f
+        self.bcs_dirac = bcs_dirac
+        self._op_cache = None
+
+    # ---- operator construction ("element-matrix assembly") -------------- #
+    def operator(self, mesh, **kwargs) -> RTOperator:
+        """Device operator for ``mesh``; rebuilt when the mesh object changes."""
+        rank, nranks = kwargs.get("rank", 0), kwargs.get("nranks", 1)
+        if self._op_cache is not None:
+            key, op = self._op_cache
+            if key[0] is mesh and key[1:] == (rank, nranks) and key[0].get_ndof() == op.flat.n_dof_global:
+                return op
+            op.close()
+        op = RTOperator(mesh, self.kappa, self.sigma, self.Phi, rank=rank, nranks=nranks)
+        self._op_cache = ((mesh, rank, nranks), op)
+        return op
+
+    def mass_matrix(self, mesh, **kwargs):
+        """+M (``mass_matrix.py:23-103``)."""
+        return TermOperator(self.operator(mesh, **kwargs), L.TERM_MASS)
+
+    def scattering_matrix(self, mesh, **kwargs):
+        """-S: the reference's ``scattering_matrix`` already carries the minus
+        sign (``scattering_matrix.py:201,222``)."""
+        return TermOperator(self.operator(mesh, **kwargs), L.TERM_SCAT)
+
+    def preconditioner_matrix(self, mesh, **kwargs):
+        """[M - S, None] (``preconditioner_matrix.py:22-114``)."""
+        return [TermOperator(self.operator(mesh, **kwargs), L.TERM_MASS | L.TERM_SCAT), None]
+
+    def interior_convection_matrix(self, mesh, **kwargs):
+        """+IC (``interior_convection_matrix.py:25-108``); ``solve`` subtracts it."""
+        return TermOperator(self.operator(mesh, **kwargs), L.TERM_ICONV, sign=-1.0)
+
+    def boundary_convection_matrix(self, mesh, **kwargs):
+        """+BC (``boundary_convection_matrix.py:27-158``)."""
+        return TermOperator(self.operator(mesh, **kwargs), L.TERM_BCONV)
+
+    # ---- right-hand sides (host side, once per solve) -------------------- #
+    def forcing_vector(self, mesh, **kwargs) -> np.ndarray:
+        """f_beta = (dx dy dth / 8) w_i w_j w_a f(x_i, y_j, th_a), dof order
+        (``forcing_vector.py:103-156``)."""
+        parts = []
+        for _, col in sorted(mesh.cols.items()):
+            assert col.is_lf
+            x0, y0, x1, y1 = col.pos
+            dx, dy = x1 - x0, y1 - y0
+            nx, ny = col.ndofs
+            xb, wx, yb, wy, _, _ = quad_xyth(nnodes_x=nx, nnodes_y=ny)
+            X, Y = push_forward(x0, x1, xb), push_forward(y0, y1, yb)
+            for _, cell in sorted(col.cells.items()):
+                assert cell.is_lf
+                th0, th1 = cell.pos
+                nth = cell.ndofs[0]
+                _, _, _, _, thb, wth = quad_xyth(nnodes_th=nth)
+                Th = push_forward(th0, th1, thb)
+                vals = _eval_nodal(self.f, X, Y, Th)
+                scale = (dx * dy * (th1 - th0) / 8.) * (
+                    np.asarray(wx).reshape(nx, 1, 1) * np.asarray(wy).reshape(1, ny, 1)
+                    * np.asarray(wth).reshape(1, 1, nth))
+                parts.append((scale * vals).reshape(-1))
+        return np.concatenate(parts)
+
+    def boundary_conditions_vector(self, mesh, **kwargs) -> np.ndarray:
+        """g_beta = bcs(x_i, y_j, th_a) at every node, dof order; optional
+        Dirac-delta handling (``boundary_conditions_vector.py:101-207``)."""
+        bcs, dirac = self.bcs_dirac
+        parts = []
+        for _, col in sorted(mesh.cols.items()):
+            assert col.is_lf
+            x0, y0, x1, y1 = col.pos
+            nx, ny = col.ndofs
+            xb, _, yb, _, _, _ = quad_xyth(nnodes_x=nx, nnodes_y=ny)
+            X, Y = push_forward(x0, x1, xb), push_forward(y0, y1, yb)
+            for _, cell in sorted(col.cells.items()):
+                assert cell.is_lf
+                th0, th1 = cell.pos
+                nth = cell.ndofs[0]
+                _, _, _, _, thb, _ = quad_xyth(nnodes_th=nth)
+                Th = push_forward(th0, th1, thb)
+                if not any(dirac):
+                    parts.append(_eval_nodal(bcs, X, Y, Th).reshape(-1))
+                    continue
+                # Dirac source: sample at the source location, weight by the
+                # (clipped) cardinal functions there.
+                lo, hi, nodes = (x0, y0, th0), (x1, y1, th1), (xb, yb, thb)
+                inside, ref = [True] * 3, [None] * 3
+                for d in range(3):
+                    if dirac[d] is not None:
+                        if dirac[d] < lo[d] or hi[d] < dirac[d]:
+                            inside[d] = False
+                        else:
+                            ref[d] = pull_back(lo[d], hi[d], dirac[d])
+                vals = np.zeros((nx, ny, nth))
+                if any(inside):
+                    grids = (X, Y, Th)
+
+                    def factor(d, k):
+                        if dirac[d] is not None and inside[d]:
+                            return max(0.0, lag_eval(nodes[d], k, ref[d])), dirac[d]
+                        return 1., grids[d][k]
+
+                    for i in range(nx):
+                        pi, xi = factor(0, i)
+                        for j in range(ny):
+                            pj, yj = factor(1, j)
+                            for a in range(nth):
+                                pa, ta = factor(2, a)
+                                vals[i, j, a] = bcs(xi, yj, ta) * pi * pj * pa
+                parts.append(vals.reshape(-1))
+        return np.concatenate(parts)
+
+    # ---- solve ------------------------------------------------------------ #
+    def solve(self, mesh, **kwargs) -> list:
+        """Assemble the element tables, restrict to interior DoFs, build the
+        right-hand side ``f_i - A_ib g_b`` and run GMRES(50) on the device
+        (``solve.py:21-149``).  Returns ``[uh_proj, convergence_info,
+        matrix_info]`` like the reference.
+
+        Extra keyword arguments (all optional): ``rtol``, ``atol``, ``max_it``,
+        ``restart``, ``orth`` override the reference's fixed KSP settings;
+        ``return_vector=True`` appends the dof-order solution vector.
+        """
+        opts = {"verbose": False, "ksp_type": "gmres", "pc_type": "bjacobi", **kwargs}
+        if opts["ksp_type"] not in ("gmres", "fgmres"):
+            raise ValueError("unsupported ksp_type %r (gmres, fgmres)" % opts["ksp_type"])
+        t0 = perf_counter()
+        op = self.operator(mesh, **{k: v for k, v in kwargs.items() if k in ("rank", "nranks")})
+        t_tables = perf_counter() - t0
+
+        f_vec = self.forcing_vector(mesh, **kwargs)
+        g_vec = self.boundary_conditions_vector(mesh, **kwargs)
+        t_rhs = perf_counter() - t0 - t_tables
+
+        # interior / inflow-boundary split on the device (split_vector.py:15-48)
+        f_i = op.mask_slab(op.to_slab(f_vec), "interior")
+        g_b = op.mask_slab(op.to_slab(g_vec), "boundary")
+        # rhs = f_i - A_ib g_b  (solve.py:67-69)
+        rhs = f_i - op.apply_slab(g_b, None, L.TERM_ALL, True)
+        x = f_i.clone()                                   # initial guess = forcing (solve.py:72)
+
+        rtol = opts.get("rtol", consts.EPS)
+        atol = opts.get("atol", consts.EPS)
+        divtol = float(np.sqrt(consts.INF))
+        max_it = int(opts.get("max_it", 5000))
+        restart = int(opts.get("restart", 50))
+        pc_type = opts["pc_type"]
+        pc = 1 if pc_type in ("bjacobi_b200", "node_bjacobi") else 0
+        t1 = perf_counter()
+        info = op.gmres(rhs, x, restart=restart, max_it=max_it, rtol=rtol, atol=atol,
+                        divtol=divtol, orth=int(opts.get("orth", 0)), pc=pc, x0_nonzero=True)
+        import torch
+        torch.cuda.synchronize(op.device)
+        t_solve = perf_counter() - t1
+
+        uh_vec = op.from_slab(x + g_b).cpu().numpy()      # merge_vectors.py:14-56
+        uh_proj = Projection(mesh).from_vector(uh_vec)
+
+        hist = info["history"]
+        convergence_info = {"converged_reason": info["reason"],
+                            "convergence_history": hist.tolist(),
+                            "iteration_number": info["iterations"],
+                            "res_f": info["res_norm"],
+                            "res_best": float(np.min(hist)) if hist.size else info["res_norm"],
+                            "rtol": rtol, "atol": atol, "divtol": divtol, "max_it": max_it}
+        matrix_info = {"extreme_singular_values": [info["sigma_max"], info["sigma_min"]],
+                       "ndof": op.n, "ndof_interior": int(op.flat.interior_mask_dof().sum()),
+                       "layout": op.flat.stats(), "true_residual_norm": info["true_res_norm"],
+                       "operator_applies": info["n_apply"],
+                       "ksp_type": opts["ksp_type"], "pc_type_requested": pc_type,
+                       "pc_type_used": "node_bjacobi" if pc else "none",
+                       "time_tables_s": t_tables, "time_rhs_s": t_rhs, "time_solve_s": t_solve}
+        if opts["verbose"]:
+            cond = info["sigma_max"] / info["sigma_min"] if info["sigma_min"] else consts.INF
+            print("Solve {} - {} finished.\n".format(pc_type, opts["ksp_type"])
+                  + 12 * " " + "Converged Reason: {}\n".format(info["reason"])
+                  + 12 * " " + "Iteration count:  {}\n".format(info["iterations"])
+                  + 12 * " " + "Final residual:   {:.4E}\n".format(info["res_norm"])
+                  + 12 * " " + "Condition Number: {:.4E}\n".format(cond)
+                  + 12 * " " + "Time Elapsed:   {:8.4f} [s]\n".format(t_solve))
+        out = [uh_proj, convergence_info, matrix_info]
+        if opts.get("return_vector"):
+            out.append(uh_vec)
+        return out

@@ -1,0 +1,103 @@
+"""numpy emulation of the k_apply kernel, reading the same FlatMesh tables.
+
+Test helper only: it lets the CPU test-suite check the host-built device tables
+(face tables, mortar pools, angular coupling, masks, slab layout) and the
+kernel's algorithm against the oracle without a GPU.  It is deliberately a
+line-by-line transliteration of ``csrc/apply.cu`` (slow Python loops; small
+meshes only) and is not part of the product.
+"""
+import numpy as np
+
+MASS, SCAT, ICONV, BCONV, ALL = 1, 2, 4, 8, 15
+
+
+def apply_slab(flat, g_off, g_pool, coef, x, terms=ALL, interior_only=False, ghost=None):
+    f = flat
+    y = np.zeros_like(x)
+    P = f.n_theta_pool
+    MAXN = f.lgl_w.shape[1]
+    for c in range(f.n_col):
+        nx, ny = int(f.col_nx[c]), int(f.col_ny[c])
+        nn = nx * ny
+        sg = int(f.col_sig[c])
+        nt, ntp = int(f.sig_nt[sg]), int(f.sig_ntp[sg])
+        soff = int(f.col_slab_off[c])
+        tp0 = int(f.sig_th0[sg])
+        hdx, hdy = 0.5 * f.col_dx[c], 0.5 * f.col_dy[c]
+        bdry = int(f.col_bdry[c])
+        mk = coef[f.col_coef_off[c]: f.col_coef_off[c] + nn]
+        ms = coef[f.col_coef_off[c] + nn: f.col_coef_off[c] + 2 * nn]
+        Gt = g_pool[g_off[sg]: g_off[sg] + ntp * ntp].reshape(ntp, ntp)
+        u = x[soff: soff + nn * ntp].reshape(nn, ntp)
+        wx, wy = f.lgl_w[nx], f.lgl_w[ny]
+        Sx, Sy = f.lgl_s[nx], f.lgl_s[ny]
+        for th in range(nt):
+            bits = int(f.th_bits[tp0 + th])
+            wt, ct, st = f.th_wt[tp0 + th], f.th_ct[tp0 + th], f.th_st[tp0 + th]
+            fa = np.zeros((4, MAXN))
+            if terms & BCONV:
+                cell = int(f.th_cell[tp0 + th])
+                r = (bits >> 8) & 0xff
+                nth0 = int(f.cell_nth[f.sig_cell0[sg] + cell])
+                for F in range(4):
+                    if (bits >> F) & 1 or (bdry >> F) & 1:
+                        continue
+                    n0 = nx if F & 1 else ny
+                    half = hdx if F & 1 else hdy
+                    for slot in range(2):
+                        fidx = c * 8 + F * 2 + slot
+                        base = int(f.face_base[fidx])
+                        if base == -1:
+                            continue
+                        src, b0 = (x, base) if base >= 0 else (ghost, -(base + 2))
+                        rs, n1 = int(f.face_rstride[fidx]), int(f.face_n1[fidx])
+                        E = f.exy_pool[f.face_exy[fidx]: f.face_exy[fidx] + n1 * n0].reshape(n1, n0)
+                        acp = f.acpl_pool[f.face_acpl[fidx] + cell * 6: f.face_acpl[fidx] + cell * 6 + 6]
+                        for j1 in range(n1):
+                            tmp = 0.0
+                            for k in range(2):
+                                eo, t1, n1t = int(acp[k * 3]), int(acp[k * 3 + 1]), int(acp[k * 3 + 2])
+                                for a in range(n1t):
+                                    tmp += f.eth_pool[eo + a * nth0 + r] * src[b0 + j1 * rs + t1 + a]
+                            tmp *= half
+                            fa[F, :n0] += E[j1, :] * tmp
+            wF = [f.th_wF[F, tp0 + th] for F in range(4)]
+            for n in range(nn):
+                i, j = divmod(n, ny)
+                u0 = u[n, th]
+                v = 0.0
+                if terms & SCAT:
+                    v = -ms[n] * float(Gt[:, th] @ u[n, :])
+                if terms & MASS:
+                    v += mk[n] * wt * u0
+                if terms & ICONV:
+                    sx = float(Sx[i, :nx] @ u[j::ny, th][:nx])
+                    sy = float(Sy[j, :ny] @ u[i * ny:(i + 1) * ny, th])
+                    v -= hdy * wy[j] * ct * sx + hdx * wx[i] * st * sy
+                masked = False
+                if i == nx - 1:
+                    if terms & BCONV:
+                        v += hdy * wy[j] * wF[0] * u0 if bits & 1 else fa[0, j]
+                    masked |= bool(bdry & 1) and bool(bits & 16)
+                if j == ny - 1:
+                    if terms & BCONV:
+                        v += hdx * wx[i] * wF[1] * u0 if bits & 2 else fa[1, i]
+                    masked |= bool(bdry & 2) and bool(bits & 32)
+                if i == 0:
+                    if terms & BCONV:
+                        v += hdy * wy[j] * wF[2] * u0 if bits & 4 else fa[2, j]
+                    masked |= bool(bdry & 4) and bool(bits & 64)
+                if j == 0:
+                    if terms & BCONV:
+                        v += hdx * wx[i] * wF[3] * u0 if bits & 8 else fa[3, i]
+                    masked |= bool(bdry & 8) and bool(bits & 128)
+                y[soff + n * ntp + th] = 0.0 if (interior_only and masked) else v
+    return y
+
+
+def host_tables(flat, problem):
+    """(g_off, g_pool, coef) exactly as RTOperator builds them, without a GPU."""
+    from rt_b200.rt.operator import build_g_pool, sample_coefficients
+    g_off, g_pool = build_g_pool(flat, problem.Phi)
+    coef = sample_coefficients(flat, problem.kappa, problem.sigma)
+    return g_off, g_pool, coef
