@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""Benchmark of the transport-operator hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload c4|c4-small|...]
+
+A "step" is ONE application of the interior transport operator
+y = A_ii x = [+BC - IC + M - S] x (all four terms, rows of inflow-boundary DoFs
+zeroed) to one synthetic vector on the workload mesh.  The default workload is
+BASELINE.json configs[3]: uniform 256 x 256 spatial columns x 32 angular cells,
+p = 4 (ndofs [5, 5, 5]) -> 262 144 000 DoF, coefficients of the
+two-strong-scatterers experiment (kappa 0..200, sigma = 0.7 kappa, normalised
+HG g = 0.8), x ~ N(0, 1).
+
+One JSON line is printed by rank 0:
+  value      whole-job GDoF/s with x already resident in HBM in slab order
+  e2e        the same metric through the reference-facing call
+             ``RTOperator.mult(x_host)`` (dof-order HOST vectors: pinned H2D copy,
+             layout conversion, apply, conversion back, D2H copy, all timed)
+  roofline   dominant kernel (k_apply) against the measured HBM copy bandwidth,
+             algorithmic traffic 16 B/DoF (read x once, write y once); the FP64
+             bound of the dense angular scattering is reported next to it
+  cpu_baseline  the oracle's CPU restatement of the reference path (scipy CSR
+             SpMV of the assembled A_ii) on a bounded sample of the workload
+  gmres      restarted-GMRES Arnoldi step timing on the same mesh
+
+``--impl reference`` times the reference's own way of applying the operator on
+the host: the explicitly assembled sparse matrix (assembled by the oracle
+restatement of src/rt, the reference being pure Python that cannot travel to
+the GPU box) multiplied with scipy CSR SpMV on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nref_spt, nref_ang, ndofs)
+    "c4": (8, 5, [5, 5, 5]),          # 256x256 cols x 32 cells, p=4: 2.62e8 DoF (BASELINE configs[3])
+    "c4-128": (7, 5, [5, 5, 5]),      # 6.55e7 DoF
+    "c4-64": (6, 5, [5, 5, 5]),       # 1.64e7 DoF
+    "c1": (2, 2, [4, 4, 4]),          # 4096 DoF (BASELINE configs[0] mesh)
+}
+LS = [3.0, 2.0]
+BYTES_PER_DOF = 16.0                  # read x + write y, FP64
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+FP64_PEAK_TFLOPS = 37.1   # measured on this pool with scripts/micro/fp64_peak.cu (DMMA and DFMA)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+_CPU = {}
+
+
+def _cpu_part(i):
+    b = _CPU["bounds"]
+    y = np.frombuffer(_CPU["y"], dtype=np.float64)
+    x = np.frombuffer(_CPU["x"], dtype=np.float64)
+    y[b[i]:b[i + 1]] = _CPU["blocks"][i] @ x
+    return i
+
+
+def cpu_reference_arm(nproc: int, sample=(3, 5, [5, 5, 5]), reps: int = 5):
+    """Assemble A_ii for a bounded sample of the workload with the oracle and time
+    CSR SpMV on `nproc` host cores (one forked process per row block; scipy's
+    SpMV is single-threaded and holds the GIL)."""
+    import multiprocessing as mp
+    import rt_b200  # noqa: F401
+    from rt_b200 import configs
+    from oracle import rt_oracle as O
+    ns, na, nd = sample
+    prob = configs.two_strong_scatterers(LS)
+    mesh = configs.build_mesh(LS, [False, False], nd, nref_ang=na, nref_spt=ns)
+    t0 = time.perf_counter()
+    sysm = O.assemble(mesh, prob.kappa, prob.sigma, prob.Phi)
+    A_ii, _ = O.restrict(sysm["A"], sysm["mask"])
+    t_asm = time.perf_counter() - t0
+    n = A_ii.shape[0]
+    ctx = mp.get_context("fork")
+    _CPU["x"] = ctx.RawArray("d", n)
+    _CPU["y"] = ctx.RawArray("d", n)
+    x = np.frombuffer(_CPU["x"], dtype=np.float64)
+    x[:] = np.random.default_rng(1).standard_normal(n)
+    y = np.frombuffer(_CPU["y"], dtype=np.float64)
+    # row blocks with equal numbers of non-zeros
+    cum = A_ii.indptr
+    bounds = np.searchsorted(cum, np.linspace(0, cum[-1], nproc + 1)).astype(int)
+    bounds[0], bounds[-1] = 0, n
+    _CPU["bounds"] = bounds
+    _CPU["blocks"] = [A_ii[bounds[i]:bounds[i + 1]] for i in range(nproc)]
+    ts = []
+    if nproc == 1:
+        _cpu_part(0)
+        for _ in range(reps):
+            t = time.perf_counter(); _cpu_part(0); ts.append(time.perf_counter() - t)
+    else:
+        with ctx.Pool(nproc) as pool:
+            pool.map(_cpu_part, range(nproc), chunksize=1)
+            for _ in range(reps):
+                t = time.perf_counter()
+                pool.map(_cpu_part, range(nproc), chunksize=1)
+                ts.append(time.perf_counter() - t)
+    ok = bool(np.allclose(y, A_ii @ x))
+    _CPU.clear()
+    assert ok
+    return {"n": int(n), "nnz": int(A_ii.nnz), "t_apply_s": float(min(ts)),
+            "t_apply_med_s": float(np.median(ts)), "t_assemble_s": float(t_asm),
+            "sample": "uniform %dx%d columns x %d cells, ndofs %s (%d interior DoF, nnz %d); "
+                      "oracle-assembled A_ii, scipy CSR SpMV in %d row-block process(es)"
+                      % (2 ** ns, 2 ** ns, 2 ** na, nd, n, A_ii.nnz, nproc)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    ns, na, nd = WORKLOADS[args.workload]
+    sample = (min(ns, 3), na, nd)
+    # warm-up + steps: each step = best-of-reps SpMV of the bounded sample
+    res = None
+    ts = []
+    for it in range(args.warmup + args.steps):
+        res = cpu_reference_arm(cores, sample, reps=3) if res is None else res
+        if it >= args.warmup:
+            ts.append(res["t_apply_med_s"])
+    gdofs = res["n"] / np.mean(ts) / 1e9
+    line = {"impl": "reference", "metric": "transport_operator_apply_throughput",
+            "value": gdofs, "unit": "GDoF/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": float(np.mean(ts) * 1e3),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "note": "CPU arm runs a bounded sample of the "
+                       "workload; throughput per DoF is size-independent for CSR SpMV"},
+            "cpu_baseline": {"value": gdofs, "unit": "GDoF/s", "cores": cores, "kind": "port",
+                             "sample": res["sample"], "assemble_s": res["t_assemble_s"]},
+            "e2e": {"value": gdofs, "unit": "GDoF/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import rt_b200  # noqa: F401
+    from rt_b200 import configs
+    from rt_b200.dg.flatmesh import FlatMesh, MeshArrays
+    from rt_b200.rt import RTOperator
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    ns, na, nd = WORKLOADS[args.workload]
+    prob = configs.two_strong_scatterers(LS)
+    t0 = time.perf_counter()
+    arrays = MeshArrays.uniform(LS, ns, na, nd)
+    flat = FlatMesh(arrays, rank=rank, nranks=world)
+    op = RTOperator(flat, prob.kappa, prob.sigma, prob.Phi, device=dev)
+    t_build = time.perf_counter() - t0
+    if world > 1:
+        op.comm_init(rank, world)
+    n_total = flat.n_dof_global
+    n_intr_local = int(flat.interior_mask_dof().sum()) if flat.n_dof <= 5_000_000 else None
+
+    gen = torch.Generator(device=dev); gen.manual_seed(1 + rank)
+    x = torch.randn(op.n_slab, dtype=torch.float64, device=dev, generator=gen)
+    op.mask_slab(x, "interior")
+    y = op.empty_slab()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    step = lambda: op.apply_slab(x, y, 15, True)          # noqa: E731
+    for _ in range(args.warmup):
+        step()
+    l0 = op.launch_count()
+    with ClockSampler(local) as clk:
+        ms_total = timed(step, args.steps)
+    launches = op.launch_count() - l0
+    ms_step = ms_total / args.steps
+    gdofs = n_total / ms_step / 1e6
+    clocks = clk.summary()
+
+    # same step without the dense angular scattering (pure streaming terms)
+    step_ns = lambda: op.apply_slab(x, y, 13, True)       # noqa: E731
+    for _ in range(2):
+        step_ns()
+    ms_ns = timed(step_ns, max(3, args.steps // 2)) / max(3, args.steps // 2)
+
+    hbm_peak, peak_src = measured_peaks()
+    achieved = BYTES_PER_DOF * (n_total / world) / (ms_step * 1e-3) / 1e9     # GB/s per GPU
+    nt = int(flat.sig_nt.max())
+    scat_flops = 2.0 * nt * n_total
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "kernel": "k_apply",
+                "peak_source": peak_src, "algorithmic_bytes_per_dof": BYTES_PER_DOF,
+                "note": "dense angular scattering costs 2*Ntheta = %d flop/DoF, FP64-bound on "
+                        "B200; see fp64 and no_scattering" % (2 * nt),
+                "fp64": {"achieved_tflops": scat_flops / world / (ms_step * 1e-3) / 1e12,
+                         "peak_tflops": FP64_PEAK_TFLOPS,
+                         "frac": scat_flops / world / (ms_step * 1e-3) / 1e12 / FP64_PEAK_TFLOPS},
+                "no_scattering": {"ms_per_step": ms_ns,
+                                  "achieved": BYTES_PER_DOF * (n_total / world) / (ms_ns * 1e-3) / 1e9,
+                                  "frac": BYTES_PER_DOF * (n_total / world) / (ms_ns * 1e-3) / 1e9 / hbm_peak}}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as fh:
+                roofline["traffic"] = json.load(fh).get(args.workload)
+        except Exception:
+            pass
+
+    # ---- e2e: reference-facing call with host buffers ------------------- #
+    e2e = None
+    if not args.no_e2e:
+        xh = torch.empty(op.n, dtype=torch.float64).pin_memory()
+        xh.normal_(generator=torch.Generator().manual_seed(7))
+        yh = torch.empty(op.n, dtype=torch.float64).pin_memory()
+        xd = torch.empty(op.n, dtype=torch.float64, device=dev)
+        yd = torch.empty(op.n, dtype=torch.float64, device=dev)
+
+        def e2e_step():
+            xd.copy_(xh, non_blocking=True)
+            op.to_slab(xd, x)
+            op.mask_slab(x, "interior")
+            op.apply_slab(x, y, 15, True)
+            op.from_slab(y, yd)
+            yh.copy_(yd, non_blocking=True)
+
+        e2e_step()
+        k = max(2, min(args.steps, 5))
+        ms_e2e = timed(e2e_step, k) / k
+        e2e = {"value": n_total / ms_e2e / 1e6, "unit": "GDoF/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": int(op.n * 8), "d2h_bytes_per_step": int(op.n * 8),
+               "call": "to_slab + mask + apply + from_slab on pinned host vectors in dof order"}
+        del xh, yh, xd, yd
+
+    # ---- GMRES Arnoldi timing on the same mesh --------------------------- #
+    gm = None
+    if not args.no_gmres:
+        try:
+            free, _ = torch.cuda.mem_get_info(dev)
+            restart = 50
+            need = (restart + 4) * op.n_slab * 8
+            if need > 0.9 * free:
+                restart = max(5, int(0.9 * free / (op.n_slab * 8)) - 4)
+            b = x.clone()
+            sol = op.zeros_slab()
+            info = op.gmres(b, sol, restart=restart, max_it=restart, rtol=1e-30, atol=0.0,
+                            orth=2, x0_nonzero=False)     # warm-up cycle
+            sol.zero_()
+            barrier()
+            t = time.perf_counter()
+            info = op.gmres(b, sol, restart=restart, max_it=restart, rtol=1e-30, atol=0.0,
+                            orth=2, x0_nonzero=False)
+            barrier()
+            dt = time.perf_counter() - t
+            its = max(info["iterations"], 1)
+            arnoldi_bytes = sum(8.0 * (2 * (k + 1) + 5) + BYTES_PER_DOF for k in range(its)) * (n_total / world)
+            gm = {"restart": restart, "iterations": its, "ms_per_iteration": dt / its * 1e3,
+                  "cycle_s": dt, "achieved_gbs": arnoldi_bytes / dt / 1e9,
+                  "frac_hbm": arnoldi_bytes / dt / 1e9 / hbm_peak,
+                  "res_reduction": info["res_norm"] / max(info["res0_norm"], 1e-300),
+                  "orth": "classical Gram-Schmidt, 1 pass (PETSc default)"}
+            op.free_workspace()
+            del b, sol
+        except Exception as exc:      # report, do not hide
+            gm = {"error": str(exc)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        r = cpu_reference_arm(1, (min(ns, 3), na, nd), reps=5)
+        cpu = {"value": r["n"] / r["t_apply_s"] / 1e9, "unit": "GDoF/s", "cores": 1,
+               "kind": "port", "sample": r["sample"], "assemble_s": r["t_assemble_s"],
+               "host_cores_available": cores}
+
+    if rank == 0:
+        line = {"metric": "transport_operator_apply_throughput", "value": gdofs,
+                "unit": "GDoF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload,
+                           "mesh": "uniform %dx%d columns x %d angular cells, ndofs %s"
+                                   % (2 ** ns, 2 ** ns, 2 ** na, nd),
+                           "ndof": int(n_total), "terms": "BC - IC + M - S, interior rows",
+                           "coefficients": "two-strong-scatterers kappa/sigma, HG g=0.8",
+                           "partition": "np.array_split of sorted column keys over %d rank(s)" % world,
+                           "l2": "vectors of %.2f GB per GPU exceed the 126 MB L2; no flush needed"
+                                 % (op.n_slab * 8 / 1e9),
+                           "table_build_s": t_build},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+                "e2e": e2e, "gmres": gm, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    op.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gmres", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
