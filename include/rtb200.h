@@ -115,7 +115,8 @@ typedef struct rtb200_flatmesh {
     const int32_t* sig_ncell;
     const int32_t* sig_cell0;   /* first entry in the sigcell arrays             */
     const int64_t* sig_th0;     /* first entry in the per-theta arrays           */
-    const int64_t* sig_g_off;   /* first entry in g_pool ([ntp][ntp], G^T)       */
+    const int64_t* sig_g_off;   /* first entry in g_pool: G[theta][theta'] row-major,
+                                   zero-padded to [8*ceil(nt/8)][8*ceil(nt/8)]   */
 
     /* per signature cell [n_sigcell], sorted-key order inside a signature */
     const int32_t* cell_nth;
@@ -134,7 +135,7 @@ typedef struct rtb200_flatmesh {
                                    of the dof inside its cell                    */
 
     /* pools */
-    int64_t n_g_pool;     const double*  g_pool;    /* per signature G^T, [theta'][theta] */
+    int64_t n_g_pool;     const double*  g_pool;    /* per signature G, [theta][theta']   */
     int64_t n_exy_pool;   const double*  exy_pool;  /* spatial mortars E^x / E^y          */
     int64_t n_eth_pool;   const double*  eth_pool;  /* (dtheta0/2) * E^theta blocks [a][r]*/
     int64_t n_acpl_pool;  const int32_t* acpl_pool; /* per (sig0, sig1, F): [ncell0][2][3]

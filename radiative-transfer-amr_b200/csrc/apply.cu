@@ -2,10 +2,8 @@
 //
 //   y = [ +BC - IC + M - S ] x           (reference: src/rt/solve.py:52)
 //
-// One thread block owns one spatial column.  The column's slab
-// u[node][theta] (node = i*ny + j, theta over all angular cells of the column)
-// is staged once in shared memory; each thread then owns one angular DoF
-// "theta" and produces y[node][theta] for every spatial node of the column:
+// Terms (per column slab u[node][theta], node = i*ny + j, theta over all angular
+// cells of the column):
 //
 //   scattering  -ms[node] * sum_theta' G[theta][theta'] u[node][theta']
 //               (dense in angle per spatial node; preconditioner_matrix.py:154-248)
@@ -20,180 +18,329 @@
 //
 // x is read once from DRAM (neighbour traces hit L2: columns are launched in
 // memory order) and y is written once: 16 B/DoF of algorithmic traffic.
-// Lanes of a warp walk consecutive theta, so slab rows are read and written
-// fully coalesced and shared-memory accesses are conflict free; the u values
-// of the scattering contraction are warp-wide broadcasts.
 #include "rtb200_internal.cuh"
 
 #include <algorithm>
 #include <map>
+#include <tuple>
 
 __constant__ double c_w[(RT_MAXN + 1) * RT_MAXN];
 __constant__ double c_s[(RT_MAXN + 1) * RT_MAXN * RT_MAXN];
 
 // --------------------------------------------------------------------------- //
-// apply kernel.  N > 0: nx == ny == N known at compile time, loops unrolled and
-// accumulators in registers.  N == 0: any nx, ny (run-time loops).  RC = number
-// of spatial nodes whose accumulators are carried through one pass over G.
+// apply kernel
+//
+// One thread block (256 threads, 8 warps) owns a GROUP of up to CG columns of
+// the same class (nx, ny, angular signature), so that they share G.  Phases:
+//
+//   0  stage the group's slabs in shared memory (cp.async, 16-byte chunks);
+//      rows are padded to a stride = 8 (mod 16) doubles so that the DMMA
+//      A-fragment loads of phase 2 are bank-conflict free.
+//   1  streaming terms, one thread per (column, theta): mass, volume
+//      convection and face fluxes for every spatial node -> y (global,
+//      coalesced along theta).  Inflow traces of neighbour columns come from
+//      global memory (L2 hits: columns are processed in memory order).
+//   2  scattering as a GEMM on the FP64 tensor cores (mma.sync m8n8k4, DMMA):
+//        ACC[row][theta] = sum_theta' U[row][theta'] * G[theta][theta'],
+//      row = (column in group, node); M = CG*nn rows in <= 8 m-tiles per
+//      chunk, warp w owns n-tiles w, w+8, ...; A fragments from shared memory,
+//      B fragments straight from G in global memory (L1/L2 resident).
+//   3  epilogue in the accumulator layout: y -= ms[node] * ACC (read-modify-
+//      write of the y values phase 1 just wrote: L2 hits, no DRAM traffic).
+//
+// N > 0: nx == ny == N at compile time (phase-1 loops unrolled); N == 0: any.
 // --------------------------------------------------------------------------- //
-template <int N, int RC>
-__global__ void __launch_bounds__(256)
-k_apply(DevMesh m, unsigned terms, int interior_only, const double* __restrict__ x,
-        const double* __restrict__ ghost, double* __restrict__ y,
-        const int32_t* __restrict__ cols) {
-    extern __shared__ __align__(16) double u_s[];
-    constexpr int NF = N > 0 ? N : RT_MAXN;
+constexpr int AP_THREADS = 256;
+constexpr int AP_WARPS = AP_THREADS / 32;
+constexpr int AP_NTB = 3;     // n-tiles per warp per pass
+constexpr int AP_MAXCG = 8;   // columns per group
 
-    const int c = cols[blockIdx.x];
-    const int nx = N > 0 ? N : m.col_nx[c];
-    const int ny = N > 0 ? N : m.col_ny[c];
+// columns per group and m-tiles per chunk for the compile-time sizes
+// (CG*nn <= 64 rows; generic kernels loop over chunks of 8 m-tiles)
+__host__ __device__ constexpr int ap_cg(int nn) { return nn >= 64 ? 1 : (64 / nn > AP_MAXCG ? AP_MAXCG : 64 / nn); }
+__host__ __device__ constexpr int ap_mt(int n) { return n == 0 ? 8 : (ap_cg(n * n) * n * n + 7) / 8; }
+
+struct GroupTab {
+    const int32_t* grp_first;   // [n_groups] first entry in grp_cols
+    const int32_t* grp_count;   // [n_groups]
+    const int32_t* grp_cols;    // column indices
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ bool dof_masked(int i, int j, int nx, int ny, int bdry, int bits) {
+    return ((i == nx - 1) && (bdry & 1) && (bits & 16)) || ((j == ny - 1) && (bdry & 2) && (bits & 32)) ||
+           ((i == 0) && (bdry & 4) && (bits & 64)) || ((j == 0) && (bdry & 8) && (bits & 128));
+}
+
+template <int N>
+__global__ void __launch_bounds__(AP_THREADS, 2)
+k_apply(DevMesh m, GroupTab gt, unsigned terms, int interior_only, const double* __restrict__ x,
+        const double* __restrict__ ghost, double* __restrict__ y, int ntps) {
+    extern __shared__ __align__(16) double u_s[];
+    __shared__ int s_col[AP_MAXCG];
+    constexpr int NF = N > 0 ? N : RT_MAXN;
+    constexpr int AP_MT = ap_mt(N);
+
+    const int g = blockIdx.x;
+    const int cg_n = gt.grp_count[g];
+    if (threadIdx.x < cg_n) s_col[threadIdx.x] = gt.grp_cols[gt.grp_first[g] + threadIdx.x];
+    __syncthreads();
+    const int c0 = s_col[0];
+    const int nx = N > 0 ? N : m.col_nx[c0];
+    const int ny = N > 0 ? N : m.col_ny[c0];
     const int nn = nx * ny;
-    const int sg = m.col_sig[c];
+    const int sg = m.col_sig[c0];
     const int nt = m.sig_nt[sg];
     const int ntp = m.sig_ntp[sg];
-    const int64_t soff = m.col_slab_off[c];
     const int64_t tp0 = m.sig_th0[sg];
-    const double hdx = 0.5 * m.col_dx[c], hdy = 0.5 * m.col_dy[c];
-    const int bdry = m.col_bdry[c];
-    const double* __restrict__ mk = m.coef + m.col_coef_off[c];
-    const double* __restrict__ ms = mk + nn;
-    const double* __restrict__ Gt = m.g_pool + m.sig_g_off[sg];
+    const int M = cg_n * nn;
 
-    {   // stage the slab: 16-byte vector copies (slab offsets and sizes are even)
-        const double2* __restrict__ src = reinterpret_cast<const double2*>(x + soff);
-        double2* dst = reinterpret_cast<double2*>(u_s);
-        const int n2 = (nn * ntp) >> 1;
-        for (int e = threadIdx.x; e < n2; e += blockDim.x) dst[e] = src[e];
+    // ---- phase 0: stage slabs ------------------------------------------------ //
+    {
+        const int chunks = ntp >> 1;                       // 16-byte chunks per row
+        const int total = M * chunks;
+        for (int e = threadIdx.x; e < total; e += AP_THREADS) {
+            const int row = e / chunks, ch = e - row * chunks;
+            const int cg = row / nn, n = row - cg * nn;
+            cp_async16(&u_s[row * ntps + 2 * ch],
+                       x + m.col_slab_off[s_col[cg]] + (int64_t)n * ntp + 2 * ch);
+        }
+        const int padc = ntps - ntp;                       // zero the pad columns
+        for (int e = threadIdx.x; e < M * padc; e += AP_THREADS) {
+            const int row = e / padc, k = e - row * padc;
+            u_s[row * ntps + ntp + k] = 0.0;
+        }
+        cp_async_wait_all();
     }
     __syncthreads();
 
-    const double* wx = c_w + nx * RT_MAXN;
-    const double* wy = c_w + ny * RT_MAXN;
-    const double* Sx = c_s + nx * RT_MAXN * RT_MAXN;
-    const double* Sy = c_s + ny * RT_MAXN * RT_MAXN;
+    // ---- phase 1: streaming terms, one thread per (column, theta) ------------ //
+    if (terms & (RTB200_TERM_MASS | RTB200_TERM_ICONV | RTB200_TERM_BCONV)) {
+        const double* wx = c_w + nx * RT_MAXN;
+        const double* wy = c_w + ny * RT_MAXN;
+        const double* Sx = c_s + nx * RT_MAXN * RT_MAXN;
+        const double* Sy = c_s + ny * RT_MAXN * RT_MAXN;
+        for (int item = threadIdx.x; item < cg_n * ntp; item += AP_THREADS) {
+            const int cg = item / ntp, th = item - cg * ntp;
+            const int c = s_col[cg];
+            const double* us = u_s + cg * nn * ntps;
+            double* yc = y + m.col_slab_off[c] + th;
+            if (th >= nt) {
+                for (int n = 0; n < nn; ++n) yc[(int64_t)n * ntp] = 0.0;
+                continue;
+            }
+            const double hdx = 0.5 * m.col_dx[c], hdy = 0.5 * m.col_dy[c];
+            const int bdry = m.col_bdry[c];
+            const double* __restrict__ mk = m.coef + m.col_coef_off[c];
+            const int bits = m.th_bits[tp0 + th];
+            const double wt = m.th_wt[tp0 + th];
+            const double ct = m.th_ct[tp0 + th];
+            const double st = m.th_st[tp0 + th];
 
-    for (int th = threadIdx.x; th < ntp; th += blockDim.x) {
-        double* yc = y + soff + th;
-        if (th >= nt) {                       // pad column of the slab stays zero
-            for (int n = 0; n < nn; ++n) yc[(int64_t)n * ntp] = 0.0;
-            continue;
-        }
-        const int bits = m.th_bits[tp0 + th];
-        const double wt = m.th_wt[tp0 + th];
-        const double ct = m.th_ct[tp0 + th];
-        const double st = m.th_st[tp0 + th];
+            double fa[4][NF];
+#pragma unroll
+            for (int F = 0; F < 4; ++F)
+#pragma unroll
+                for (int q = 0; q < NF; ++q) fa[F][q] = 0.0;
 
-        // ---- inflow face fluxes fa[F][q], q = node index along the face ---- //
-        double fa[4][NF];
+            if (terms & RTB200_TERM_BCONV) {
+                const int cell = m.th_cell[tp0 + th];
+                const int r = (bits >> 8) & 0xff;
+                const int nth0 = m.cell_nth[m.sig_cell0[sg] + cell];
 #pragma unroll
-        for (int F = 0; F < 4; ++F)
+                for (int F = 0; F < 4; ++F) {
+                    if ((bits >> F) & 1) continue;       // outflow for this angle
+                    if ((bdry >> F) & 1) continue;       // inflow through the domain boundary
+                    const int n0 = (F & 1) ? nx : ny;
+                    const double half = (F & 1) ? hdx : hdy;
+                    const double* wq = (F & 1) ? wx : wy;
+                    const double wF = m.th_wF[F * m.n_theta_pool + tp0 + th];
+                    for (int slot = 0; slot < 2; ++slot) {
+                        const int fidx = c * 8 + F * 2 + slot;
+                        const int64_t base = m.face_base[fidx];
+                        if (base == -1) continue;
+                        const double* __restrict__ src = base >= 0 ? x + base : ghost + (-(base + 2));
+                        const int rs = m.face_rstride[fidx];
+                        const int eo = m.face_exy[fidx];
+                        const int ao = m.face_acpl[fidx];
+                        if (eo < 0 && ao < 0) {
+                            // conforming neighbour: E = diag(w), E_theta = diag(wF)
+                            const double f = half * wF;
 #pragma unroll
-            for (int q = 0; q < NF; ++q) fa[F][q] = 0.0;
-
-        if (terms & RTB200_TERM_BCONV) {
-            const int cell = m.th_cell[tp0 + th];
-            const int r = (bits >> 8) & 0xff;
-            const int nth0 = m.cell_nth[m.sig_cell0[sg] + cell];
-#pragma unroll
-            for (int F = 0; F < 4; ++F) {
-                if ((bits >> F) & 1) continue;       // outflow for this angle
-                if ((bdry >> F) & 1) continue;       // inflow through the domain boundary
-                const int n0 = (F & 1) ? nx : ny;
-                const double half = (F & 1) ? hdx : hdy;
-                for (int slot = 0; slot < 2; ++slot) {
-                    const int fidx = c * 8 + F * 2 + slot;
-                    const int64_t base = m.face_base[fidx];
-                    if (base == -1) continue;
-                    const double* __restrict__ src = base >= 0 ? x + base : ghost + (-(base + 2));
-                    const int rs = m.face_rstride[fidx];
-                    const int n1 = m.face_n1[fidx];
-                    const double* __restrict__ E = m.exy_pool + m.face_exy[fidx];
-                    const int32_t* __restrict__ acp = m.acpl_pool + m.face_acpl[fidx] + cell * 6;
-                    for (int j1 = 0; j1 < n1; ++j1) {
-                        double tmp = 0.0;
-                        for (int k = 0; k < 2; ++k) {
-                            const int n1t = acp[k * 3 + 2];
-                            if (n1t == 0) continue;
-                            const double* __restrict__ eth = m.eth_pool + acp[k * 3] + r;
-                            const double* __restrict__ tr = src + (int64_t)j1 * rs + acp[k * 3 + 1];
-                            for (int a = 0; a < n1t; ++a) tmp = fma(eth[a * nth0], tr[a], tmp);
+                            for (int q = 0; q < NF; ++q)
+                                if (q < n0) fa[F][q] = f * wq[q] * src[(int64_t)q * rs + th];
+                            continue;
                         }
-                        tmp *= half;
+                        const int n1 = m.face_n1[fidx];
+                        for (int j1 = 0; j1 < n1; ++j1) {
+                            double tmp;
+                            if (ao < 0) {
+                                tmp = wF * src[(int64_t)j1 * rs + th];
+                            } else {
+                                const int32_t* __restrict__ acp = m.acpl_pool + ao + cell * 6;
+                                tmp = 0.0;
+                                for (int k = 0; k < 2; ++k) {
+                                    const int n1t = acp[k * 3 + 2];
+                                    if (n1t == 0) continue;
+                                    const double* __restrict__ eth = m.eth_pool + acp[k * 3] + r;
+                                    const double* __restrict__ tr = src + (int64_t)j1 * rs + acp[k * 3 + 1];
+                                    for (int a = 0; a < n1t; ++a) tmp = fma(eth[a * nth0], tr[a], tmp);
+                                }
+                            }
+                            tmp *= half;
+                            if (eo < 0) {
 #pragma unroll
-                        for (int q = 0; q < NF; ++q)
-                            if (q < n0) fa[F][q] = fma(E[j1 * n0 + q], tmp, fa[F][q]);
+                                for (int q = 0; q < NF; ++q)
+                                    if (q == j1) fa[F][q] = fma(wq[q], tmp, fa[F][q]);
+                            } else {
+                                const double* __restrict__ E = m.exy_pool + eo;
+#pragma unroll
+                                for (int q = 0; q < NF; ++q)
+                                    if (q < n0) fa[F][q] = fma(E[j1 * n0 + q], tmp, fa[F][q]);
+                            }
+                        }
                     }
+                }
+            }
+            const double wF0 = m.th_wF[0 * m.n_theta_pool + tp0 + th];
+            const double wF1 = m.th_wF[1 * m.n_theta_pool + tp0 + th];
+            const double wF2 = m.th_wF[2 * m.n_theta_pool + tp0 + th];
+            const double wF3 = m.th_wF[3 * m.n_theta_pool + tp0 + th];
+
+#pragma unroll
+            for (int i = 0; i < NF; ++i) {
+                if (i >= nx) break;
+#pragma unroll
+                for (int j = 0; j < NF; ++j) {
+                    if (j >= ny) break;
+                    const int n = i * ny + j;
+                    const double u0 = us[n * ntps + th];
+                    double v = 0.0;
+                    if (terms & RTB200_TERM_MASS) v = mk[n] * wt * u0;
+                    if (terms & RTB200_TERM_ICONV) {
+                        double sx = 0.0, sy = 0.0;
+#pragma unroll
+                        for (int k = 0; k < NF; ++k)
+                            if (k < nx) sx = fma(Sx[i * RT_MAXN + k], us[(k * ny + j) * ntps + th], sx);
+#pragma unroll
+                        for (int k = 0; k < NF; ++k)
+                            if (k < ny) sy = fma(Sy[j * RT_MAXN + k], us[(i * ny + k) * ntps + th], sy);
+                        v -= hdy * wy[j] * ct * sx + hdx * wx[i] * st * sy;
+                    }
+                    if (terms & RTB200_TERM_BCONV) {
+                        if (i == nx - 1) v += (bits & 1) ? hdy * wy[j] * wF0 * u0 : fa[0][j];
+                        if (j == ny - 1) v += (bits & 2) ? hdx * wx[i] * wF1 * u0 : fa[1][i];
+                        if (i == 0) v += (bits & 4) ? hdy * wy[j] * wF2 * u0 : fa[2][j];
+                        if (j == 0) v += (bits & 8) ? hdx * wx[i] * wF3 * u0 : fa[3][i];
+                    }
+                    const bool masked = interior_only && dof_masked(i, j, nx, ny, bdry, bits);
+                    yc[(int64_t)n * ntp] = masked ? 0.0 : v;
                 }
             }
         }
-        const double wF0 = m.th_wF[0 * m.n_theta_pool + tp0 + th];
-        const double wF1 = m.th_wF[1 * m.n_theta_pool + tp0 + th];
-        const double wF2 = m.th_wF[2 * m.n_theta_pool + tp0 + th];
-        const double wF3 = m.th_wF[3 * m.n_theta_pool + tp0 + th];
+    }
+    if (!(terms & RTB200_TERM_SCAT)) return;
+    __syncthreads();        // phase-1 stores to y are visible to the whole block
 
-        // ---- nodes, RC at a time ------------------------------------------ //
-        for (int nb = 0; nb < nn; nb += RC) {
-            double acc[RC];
-#pragma unroll
-            for (int r = 0; r < RC; ++r) acc[r] = 0.0;
+    // ---- phase 2 + 3: scattering GEMM on DMMA, read-modify-write epilogue ----- //
+    // K is walked in steps of 8: DMMA "even" uses theta' = 8s + {0,2,4,6}, DMMA
+    // "odd" uses 8s + {1,3,5,7}, so that every lane fetches its two operands of a
+    // step pair with ONE 16-byte load (A from shared memory, B from G).
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int lr = lane >> 2, lk = lane & 3;
+        const int k8 = (nt + 7) & ~7;
+        const int n_tiles = (nt + 7) >> 3;
+        const double* __restrict__ G = m.g_pool + m.sig_g_off[sg];   // [n_tiles*8][k8]
+        const int m_tiles = (M + 7) >> 3;
+        const bool first_write = !(terms & (RTB200_TERM_MASS | RTB200_TERM_ICONV | RTB200_TERM_BCONV));
 
-            if (terms & RTB200_TERM_SCAT) {
-                // acc[r] = sum_tp G^T[tp][th] * u[nb + r][tp]; two tp per step so the
-                // u operand is one 16-byte broadcast load.
-                const double* __restrict__ g = Gt + th;
-                for (int tp = 0; tp < ntp; tp += 2) {
-                    const double g0 = g[(int64_t)tp * ntp];
-                    const double g1 = g[(int64_t)(tp + 1) * ntp];
+        for (int mc = 0; mc < m_tiles; mc += AP_MT) {              // chunks of <= 64 rows
+            const int mt_n = min(AP_MT, m_tiles - mc);
+            for (int nb = warp; nb < n_tiles; nb += AP_WARPS * AP_NTB) {   // passes over my n-tiles
+                double acc[AP_MT][AP_NTB][2];
 #pragma unroll
-                    for (int r = 0; r < RC; ++r) {
-                        const int n = (nb + r < nn) ? nb + r : nn - 1;
-                        const double2 uu = *reinterpret_cast<const double2*>(&u_s[n * ntp + tp]);
-                        acc[r] = fma(g0, uu.x, acc[r]);
-                        acc[r] = fma(g1, uu.y, acc[r]);
+                for (int a = 0; a < AP_MT; ++a)
+#pragma unroll
+                    for (int b = 0; b < AP_NTB; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+                const int nbv = min(AP_NTB, (n_tiles - nb + AP_WARPS - 1) / AP_WARPS);   // my tiles this pass
+                const double2* gp[AP_NTB];
+#pragma unroll
+                for (int b = 0; b < AP_NTB; ++b) {
+                    const int ntile = min(nb + b * AP_WARPS, n_tiles - 1);
+                    gp[b] = reinterpret_cast<const double2*>(G + (int64_t)(ntile * 8 + lr) * k8 + 2 * lk);
+                }
+                const double* ap = u_s + (mc * 8 + lr) * ntps + 2 * lk;
+
+                double2 bf[AP_NTB];
+#pragma unroll
+                for (int b = 0; b < AP_NTB; ++b) bf[b] = gp[b][0];
+                for (int s8 = 0; s8 < k8; s8 += 8) {
+                    double2 bn[AP_NTB];
+                    const int sn = (s8 + 8 < k8) ? s8 + 8 : s8;      // prefetch next step pair
+#pragma unroll
+                    for (int b = 0; b < AP_NTB; ++b) bn[b] = gp[b][sn >> 1];
+#pragma unroll
+                    for (int a = 0; a < AP_MT; ++a) {
+                        if (a < mt_n) {
+                            const double2 af = *reinterpret_cast<const double2*>(ap + a * 8 * ntps + s8);
+#pragma unroll
+                            for (int b = 0; b < AP_NTB; ++b)
+                                if (b < nbv) {
+                                    dmma_8x8x4(acc[a][b][0], acc[a][b][1], af.x, bf[b].x);
+                                    dmma_8x8x4(acc[a][b][0], acc[a][b][1], af.y, bf[b].y);
+                                }
+                        }
+                    }
+#pragma unroll
+                    for (int b = 0; b < AP_NTB; ++b) bf[b] = bn[b];
+                }
+
+                // epilogue: thread holds rows mt*8 + lr, thetas ntile*8 + 2*lk + {0, 1}
+#pragma unroll
+                for (int a = 0; a < AP_MT; ++a) {
+                    if (a >= mt_n) break;
+                    const int row = (mc + a) * 8 + lr;
+                    if (row >= M) continue;
+                    const int cg = row / nn, n = row - cg * nn;
+                    const int c = s_col[cg];
+                    const double msn = m.coef[m.col_coef_off[c] + nn + n];
+                    const int bdry = m.col_bdry[c];
+                    const int i = n / ny, j = n - i * ny;
+                    double* yr = y + m.col_slab_off[c] + (int64_t)n * ntp;
+#pragma unroll
+                    for (int b = 0; b < AP_NTB; ++b) {
+                        const int ntile = nb + b * AP_WARPS;
+                        const int th = ntile * 8 + 2 * lk;
+                        if (ntile >= n_tiles || th >= ntp) continue;
+                        double2 v = first_write ? make_double2(0.0, 0.0)
+                                                : *reinterpret_cast<const double2*>(yr + th);
+                        double s0 = -msn * acc[a][b][0], s1 = -msn * acc[a][b][1];
+                        if (interior_only) {
+                            const int b0 = m.th_bits[tp0 + th];
+                            const int b1 = (th + 1 < nt) ? m.th_bits[tp0 + th + 1] : 0;
+                            if (dof_masked(i, j, nx, ny, bdry, b0)) s0 = 0.0;
+                            if (dof_masked(i, j, nx, ny, bdry, b1)) s1 = 0.0;
+                        }
+                        if (th + 1 >= nt) s1 = 0.0;
+                        v.x += s0;
+                        v.y += s1;
+                        *reinterpret_cast<double2*>(yr + th) = v;
                     }
                 }
-            }
-
-#pragma unroll
-            for (int r = 0; r < RC; ++r) {
-                const int n = nb + r;
-                if (n >= nn) break;
-                const int i = n / ny, j = n - i * ny;
-                const double u0 = u_s[n * ntp + th];
-                double v = (terms & RTB200_TERM_SCAT) ? -ms[n] * acc[r] : 0.0;
-                if (terms & RTB200_TERM_MASS) v = fma(mk[n] * wt, u0, v);
-                if (terms & RTB200_TERM_ICONV) {
-                    double sx = 0.0, sy = 0.0;
-#pragma unroll
-                    for (int k = 0; k < NF; ++k)
-                        if (k < nx) sx = fma(Sx[i * RT_MAXN + k], u_s[(k * ny + j) * ntp + th], sx);
-#pragma unroll
-                    for (int k = 0; k < NF; ++k)
-                        if (k < ny) sy = fma(Sy[j * RT_MAXN + k], u_s[(i * ny + k) * ntp + th], sy);
-                    v -= hdy * wy[j] * ct * sx + hdx * wx[i] * st * sy;
-                }
-                bool masked = false;
-                if (i == nx - 1) {
-                    if (terms & RTB200_TERM_BCONV)
-                        v += (bits & 1) ? hdy * wy[j] * wF0 * u0 : fa[0][j];
-                    masked |= (bdry & 1) && (bits & 16);
-                }
-                if (j == ny - 1) {
-                    if (terms & RTB200_TERM_BCONV)
-                        v += (bits & 2) ? hdx * wx[i] * wF1 * u0 : fa[1][i];
-                    masked |= (bdry & 2) && (bits & 32);
-                }
-                if (i == 0) {
-                    if (terms & RTB200_TERM_BCONV)
-                        v += (bits & 4) ? hdy * wy[j] * wF2 * u0 : fa[2][j];
-                    masked |= (bdry & 4) && (bits & 64);
-                }
-                if (j == 0) {
-                    if (terms & RTB200_TERM_BCONV)
-                        v += (bits & 8) ? hdx * wx[i] * wF3 * u0 : fa[3][i];
-                    masked |= (bdry & 8) && (bits & 128);
-                }
-                yc[(int64_t)n * ntp] = (interior_only && masked) ? 0.0 : v;
             }
         }
     }
@@ -269,21 +416,29 @@ __global__ void k_mask(DevMesh m, double* __restrict__ xs, int keep) {
 // --------------------------------------------------------------------------- //
 // host side
 // --------------------------------------------------------------------------- //
-template <int N, int RC>
+static int ntps_for(int ntp) {
+    // row stride in shared memory: >= ntp rounded up to a multiple of 8 (one DMMA
+    // step pair), and = 8 (mod 16) doubles so that the 16-byte A-fragment loads of
+    // a quarter warp (2 rows x 64 B) cover all 32 banks: conflict free
+    int v = (ntp + 7) & ~7;
+    while ((v & 15) != 8) v += 8;
+    return v;
+}
+
+template <int N>
 static int launch_bucket(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int interior_only,
                          const double* x, double* y, cudaStream_t st) {
-    auto kern = k_apply<N, RC>;
-    if (b.smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)b.smem);
-        if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaFuncSetAttribute(k_apply)");
-    }
-    int threads = ((b.max_ntp + 31) / 32) * 32;
-    threads = std::max(64, std::min(256, threads));
-    kern<<<b.count, threads, b.smem, st>>>(ctx->dm, terms, interior_only, x, ctx->ghost_dev, y,
-                                           b.cols_dev);
+    auto kern = k_apply<N>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.smem);
+    if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaFuncSetAttribute(k_apply, smem)");
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaFuncSetAttribute(k_apply, carveout)");
+    GroupTab gt{b.grp_first_dev, b.grp_count_dev, b.cols_dev};
+    kern<<<b.n_groups, AP_THREADS, b.smem, st>>>(ctx->dm, gt, terms, interior_only, x,
+                                                 ctx->ghost_dev, y, b.ntps);
     ctx->launches++;
-    cudaError_t e = cudaGetLastError();
+    e = cudaGetLastError();
     if (e != cudaSuccess) return rt_cuda(ctx, e, "k_apply launch");
     return RTB200_OK;
 }
@@ -293,14 +448,14 @@ int rt_launch_apply(rtb200_ctx* ctx, unsigned terms, int interior_only, const do
     for (const Bucket& b : ctx->buckets) {
         int rc;
         switch (b.n) {
-            case 2: rc = launch_bucket<2, 4>(ctx, b, terms, interior_only, x, y, st); break;
-            case 3: rc = launch_bucket<3, 9>(ctx, b, terms, interior_only, x, y, st); break;
-            case 4: rc = launch_bucket<4, 16>(ctx, b, terms, interior_only, x, y, st); break;
-            case 5: rc = launch_bucket<5, 25>(ctx, b, terms, interior_only, x, y, st); break;
-            case 6: rc = launch_bucket<6, 18>(ctx, b, terms, interior_only, x, y, st); break;
-            case 7: rc = launch_bucket<7, 25>(ctx, b, terms, interior_only, x, y, st); break;
-            case 8: rc = launch_bucket<8, 32>(ctx, b, terms, interior_only, x, y, st); break;
-            default: rc = launch_bucket<0, 8>(ctx, b, terms, interior_only, x, y, st); break;
+            case 2: rc = launch_bucket<2>(ctx, b, terms, interior_only, x, y, st); break;
+            case 3: rc = launch_bucket<3>(ctx, b, terms, interior_only, x, y, st); break;
+            case 4: rc = launch_bucket<4>(ctx, b, terms, interior_only, x, y, st); break;
+            case 5: rc = launch_bucket<5>(ctx, b, terms, interior_only, x, y, st); break;
+            case 6: rc = launch_bucket<6>(ctx, b, terms, interior_only, x, y, st); break;
+            case 7: rc = launch_bucket<7>(ctx, b, terms, interior_only, x, y, st); break;
+            case 8: rc = launch_bucket<8>(ctx, b, terms, interior_only, x, y, st); break;
+            default: rc = launch_bucket<0>(ctx, b, terms, interior_only, x, y, st); break;
         }
         if (rc) return rc;
     }
@@ -312,31 +467,54 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
     RT_CUDA(ctx, cudaMemcpyToSymbol(c_w, m->lgl_w, sizeof(double) * (RT_MAXN + 1) * RT_MAXN));
     RT_CUDA(ctx, cudaMemcpyToSymbol(c_s, m->lgl_s,
                                     sizeof(double) * (RT_MAXN + 1) * RT_MAXN * RT_MAXN));
-    // buckets by compile-time size; column order inside a bucket = memory order
-    std::map<int, std::vector<int32_t>> by_n;
-    std::map<int, int> max_ntp;
-    std::map<int, size_t> smem;
+    // Launch buckets by compile-time size N; inside a bucket, columns of the same
+    // class (nx, ny, signature) are packed into groups of up to CG columns that
+    // share G in the scattering GEMM; one launch uses one smem row stride.
+    struct Cls { int n, nx, ny, sig; bool operator<(const Cls& o) const {
+        return std::tie(n, nx, ny, sig) < std::tie(o.n, o.nx, o.ny, o.sig); } };
+    std::map<Cls, std::vector<int32_t>> by_cls;
     for (int c = 0; c < m->n_col; ++c) {
         const int nx = m->col_nx[c], ny = m->col_ny[c];
         const int n = (nx == ny && nx >= 2 && nx <= 8) ? nx : 0;
-        by_n[n].push_back(c);
-        const int ntp = m->sig_ntp[m->col_sig[c]];
-        max_ntp[n] = std::max(max_ntp[n], ntp);
-        smem[n] = std::max(smem[n], sizeof(double) * (size_t)nx * ny * ntp);
+        by_cls[Cls{n, nx, ny, m->col_sig[c]}].push_back(c);
     }
-    for (auto& kv : by_n) {
+    std::map<int, std::vector<int32_t>> cols, first, count;
+    std::map<int, int> max_ntp;
+    std::map<int, size_t> rows_max;
+    for (auto& kv : by_cls) {
+        const Cls& k = kv.first;
+        const int nn = k.nx * k.ny;
+        int cg = ap_cg(nn);
+        auto& v = kv.second;
+        for (size_t i = 0; i < v.size(); i += cg) {
+            const int cnt = (int)std::min<size_t>(cg, v.size() - i);
+            first[k.n].push_back((int32_t)cols[k.n].size());
+            count[k.n].push_back(cnt);
+            for (int t = 0; t < cnt; ++t) cols[k.n].push_back(v[i + t]);
+            rows_max[k.n] = std::max(rows_max[k.n], (size_t)((cnt * nn + 7) / 8) * 8);
+        }
+        max_ntp[k.n] = std::max(max_ntp[k.n], m->sig_ntp[k.sig]);
+    }
+    for (auto& kv : cols) {
         Bucket b;
         b.n = kv.first;
         b.count = (int)kv.second.size();
-        b.max_ntp = max_ntp[kv.first];
-        b.smem = smem[kv.first];
+        b.n_groups = (int)first[b.n].size();
+        b.max_ntp = max_ntp[b.n];
+        b.ntps = ntps_for(b.max_ntp);
+        b.smem = sizeof(double) * rows_max[b.n] * (size_t)b.ntps;
         if (b.smem > 227 * 1024)
-            return rt_fail(ctx, RTB200_EUNSUPPORTED,
-                           "a column slab exceeds 227 KB of shared memory");
-        RT_CUDA(ctx, cudaMalloc((void**)&b.cols_dev, sizeof(int32_t) * b.count));
-        ctx->allocs.push_back(b.cols_dev);
-        RT_CUDA(ctx, cudaMemcpy(b.cols_dev, kv.second.data(), sizeof(int32_t) * b.count,
-                                cudaMemcpyHostToDevice));
+            return rt_fail(ctx, RTB200_EUNSUPPORTED, "a column slab exceeds 227 KB of shared memory");
+        auto up = [&](const std::vector<int32_t>& h, int32_t** d) -> int {
+            RT_CUDA(ctx, cudaMalloc((void**)d, sizeof(int32_t) * h.size()));
+            ctx->allocs.push_back(*d);
+            RT_CUDA(ctx, cudaMemcpy(*d, h.data(), sizeof(int32_t) * h.size(), cudaMemcpyHostToDevice));
+            return RTB200_OK;
+        };
+        int rc;
+        if ((rc = up(kv.second, &b.cols_dev))) return rc;
+        if ((rc = up(first[b.n], &b.grp_first_dev))) return rc;
+        if ((rc = up(count[b.n], &b.grp_count_dev))) return rc;
         ctx->buckets.push_back(b);
     }
     return RTB200_OK;

@@ -33,9 +33,13 @@ struct DevMesh {
 struct Bucket {
     int n = 0;                 // template selector
     int count = 0;
+    int n_groups = 0;          // thread blocks: groups of same-class columns
     int max_ntp = 0;
-    size_t smem = 0;           // bytes of dynamic shared memory (largest slab)
-    int32_t* cols_dev = nullptr;
+    int ntps = 0;              // shared-memory row stride (doubles)
+    size_t smem = 0;           // bytes of dynamic shared memory
+    int32_t* cols_dev = nullptr;        // column indices, group after group
+    int32_t* grp_first_dev = nullptr;   // [n_groups] first entry in cols_dev
+    int32_t* grp_count_dev = nullptr;   // [n_groups] columns in the group
 };
 
 struct NcclApi;                // resolved with dlopen in comm.cu

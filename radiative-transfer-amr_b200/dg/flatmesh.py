@@ -214,7 +214,7 @@ def _along(F: int) -> int:
 class FlatMesh:
     """All mesh-dependent device tables for one rank's block of columns."""
 
-    def __init__(self, arrays, rank: int = 0, nranks: int = 1):
+    def __init__(self, arrays, rank: int = 0, nranks: int = 1, conforming_fast_path: bool = True):
         from ..rt import tables as T      # late import: rt imports this module
         if not isinstance(arrays, MeshArrays):
             arrays = MeshArrays.from_mesh(arrays)
@@ -329,6 +329,11 @@ class FlatMesh:
         self.face_n1 = np.zeros(nc * 8, np.int32)
         self.face_acpl = np.zeros(nc * 8, np.int32)
         exy_pool, exy_ids = [], {}
+
+        def exy_pool_view(off, n1_, n0_):
+            flat_ = np.concatenate(exy_pool)
+            return flat_[off:off + n1_ * n0_].reshape(n1_, n0_)
+
         eth_pool, eth_ids = [], {}
         acpl_pool, acpl_ids = [], {}
         n_exy = n_eth = n_acpl = 0
@@ -394,7 +399,18 @@ class FlatMesh:
                         exy_pool.append(np.ascontiguousarray(E).reshape(-1))
                         n_exy += E.size
                     offs[u] = exy_ids[kt]
-                self.face_exy[fidx] = offs[inv]
+                eoff = offs[inv]
+                # conforming in space (same level, same order): E = diag(w) up to
+                # rounding; flagged -1 so the kernel takes its pointwise path
+                if conforming_fast_path:
+                    for u, kk in enumerate(uk):
+                        if int(kk[2]) == 0 and int(kk[0]) == int(kk[1]):
+                            n_ = int(kk[0])
+                            E = exy_pool_view(offs[u], n_, n_)
+                            w_ = np.asarray(lgl_rule(n_)[1], dtype=np.float64)
+                            if np.max(np.abs(E - np.diag(w_))) <= 1e-14:
+                                eoff = np.where(inv == u, -1, eoff)
+                self.face_exy[fidx] = eoff
 
                 # angular coupling tables per (sig0, sig1, F)
                 akey = np.stack([A.sig[g0], A.sig[g1]], axis=1)
@@ -427,7 +443,16 @@ class FlatMesh:
                         acpl_pool.append(tab.reshape(-1))
                         n_acpl += tab.size
                     offs[u] = acpl_ids[kt]
-                self.face_acpl[fidx] = offs[inv]
+                aoff = offs[inv]
+                # conforming in angle (both columns share the signature):
+                # E_theta = diag(wF) up to rounding; flagged -1
+                if conforming_fast_path:
+                    for u, kk in enumerate(uk):
+                        if int(kk[0]) == int(kk[1]) and self._acpl_is_diagonal(
+                                A.sigs[int(kk[0])], int(kk[0]), F, acpl_pool, eth_pool,
+                                acpl_ids[(int(kk[0]), int(kk[1]), F)], eth_ids):
+                            aoff = np.where(inv == u, -1, aoff)
+                self.face_acpl[fidx] = aoff
 
         self.exy_pool = np.concatenate(exy_pool) if exy_pool else np.zeros(1)
         self.eth_pool = np.concatenate(eth_pool) if eth_pool else np.zeros(1)
@@ -438,6 +463,28 @@ class FlatMesh:
         self._owner = owner
         self._slab_sz_g = slab_sz
         self._build_halo_plan()
+
+    # ------------------------------------------------------------------ #
+    def _acpl_is_diagonal(self, sig, si, F, acpl_pool, eth_pool, tab_off, eth_ids) -> bool:
+        """True when the (sig, sig, F) angular coupling is the pointwise upwind
+        weight: every inflow cell couples to the same cell only and its scaled
+        E_theta block equals diag(wF) to 1e-14."""
+        pool = np.concatenate(acpl_pool)
+        eth = np.concatenate(eth_pool)
+        o = int(self.sig_th0[si])
+        for c0 in range(len(sig.keys)):
+            ent = pool[tab_off + c0 * 6: tab_off + c0 * 6 + 6]
+            q = int(sig.quadrant[c0])
+            if q >= 0 and F in _OUTFLOW[q]:
+                continue
+            nth = int(sig.nth[c0])
+            if ent[5] != 0 or ent[2] != nth or ent[1] != int(sig.thoff[c0]):
+                return False
+            blk = eth[ent[0]: ent[0] + nth * nth].reshape(nth, nth)
+            wF = self.th_wF[F, o + int(sig.thoff[c0]): o + int(sig.thoff[c0]) + nth]
+            if np.max(np.abs(blk - np.diag(wF))) > 1e-14:
+                return False
+        return True
 
     # ------------------------------------------------------------------ #
     def _trace_rows(self, g: int, side: int):

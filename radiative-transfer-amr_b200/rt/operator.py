@@ -89,18 +89,21 @@ def sample_coefficients(flat: FlatMesh, kappa, sigma) -> np.ndarray:
 
 
 def build_g_pool(flat: FlatMesh, Phi):
-    """Per angular signature, G^T padded to [ntp][ntp] (row theta', col theta)."""
+    """Per angular signature, G[theta][theta'] row-major, zero-padded to
+    [8 * ceil(nt / 8)][8 * ceil(nt / 8)] (the scattering GEMM walks 8 output
+    angles per DMMA n-tile and 8 input angles per k-step pair)."""
     offs, parts, n = [], [], 0
     for si, s in enumerate(flat.arrays.sigs):
         o = int(flat.sig_th0[si])
         theta = flat.th_theta[o:o + s.nt]
         wt = flat.th_wt[o:o + s.nt]
         G = T.scattering_kernel(Phi, theta, wt)
-        Gt = np.zeros((s.ntp, s.ntp))
-        Gt[:s.nt, :s.nt] = G.T
+        rows = k4 = 8 * ((s.nt + 7) // 8)
+        Gp = np.zeros((rows, k4))
+        Gp[:s.nt, :s.nt] = G
         offs.append(n)
-        parts.append(Gt.reshape(-1))
-        n += Gt.size
+        parts.append(Gp.reshape(-1))
+        n += Gp.size
     return np.array(offs, np.int64), np.concatenate(parts)
 
 

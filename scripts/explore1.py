@@ -8,10 +8,10 @@ from rt_b200 import configs
 from rt_b200.rt import RTOperator
 from rt_b200.dg.flatmesh import FlatMesh, MeshArrays
 
-for case in golden_cases():
+for case in [c for c in golden_cases() if c != "hp_mixed"]:
     mesh, d, prob = load_golden(case)
     t = time.time()
-    uh, conv, minfo, u = prob.solve(mesh, pc_type="none", rtol=1e-13, atol=1e-30, max_it=30000, return_vector=True)
+    uh, conv, minfo, u = prob.solve(mesh, pc_type="none", rtol=1e-13, atol=0.0, max_it=30000, return_vector=True)
     print(case, "reason", conv["converged_reason"], "its", conv["iteration_number"], "res", conv["res_f"],
           "err", rel_err(u, d["u"]), "sv", minfo["extreme_singular_values"], "t_solve %.3f" % minfo["time_solve_s"], flush=True)
 

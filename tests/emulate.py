@@ -27,7 +27,8 @@ def apply_slab(flat, g_off, g_pool, coef, x, terms=ALL, interior_only=False, gho
         bdry = int(f.col_bdry[c])
         mk = coef[f.col_coef_off[c]: f.col_coef_off[c] + nn]
         ms = coef[f.col_coef_off[c] + nn: f.col_coef_off[c] + 2 * nn]
-        Gt = g_pool[g_off[sg]: g_off[sg] + ntp * ntp].reshape(ntp, ntp)
+        rows = k4 = 8 * ((nt + 7) // 8)
+        G = g_pool[g_off[sg]: g_off[sg] + rows * k4].reshape(rows, k4)
         u = x[soff: soff + nn * ntp].reshape(nn, ntp)
         wx, wy = f.lgl_w[nx], f.lgl_w[ny]
         Sx, Sy = f.lgl_s[nx], f.lgl_s[ny]
@@ -51,23 +52,36 @@ def apply_slab(flat, g_off, g_pool, coef, x, terms=ALL, interior_only=False, gho
                             continue
                         src, b0 = (x, base) if base >= 0 else (ghost, -(base + 2))
                         rs, n1 = int(f.face_rstride[fidx]), int(f.face_n1[fidx])
-                        E = f.exy_pool[f.face_exy[fidx]: f.face_exy[fidx] + n1 * n0].reshape(n1, n0)
-                        acp = f.acpl_pool[f.face_acpl[fidx] + cell * 6: f.face_acpl[fidx] + cell * 6 + 6]
+                        eo, ao = int(f.face_exy[fidx]), int(f.face_acpl[fidx])
+                        wq = wx if F & 1 else wy
+                        wFF = f.th_wF[F, tp0 + th]
+                        if eo < 0 and ao < 0:            # conforming fast path of the kernel
+                            for q in range(n0):
+                                fa[F, q] = half * wFF * wq[q] * src[b0 + q * rs + th]
+                            continue
                         for j1 in range(n1):
-                            tmp = 0.0
-                            for k in range(2):
-                                eo, t1, n1t = int(acp[k * 3]), int(acp[k * 3 + 1]), int(acp[k * 3 + 2])
-                                for a in range(n1t):
-                                    tmp += f.eth_pool[eo + a * nth0 + r] * src[b0 + j1 * rs + t1 + a]
+                            if ao < 0:
+                                tmp = wFF * src[b0 + j1 * rs + th]
+                            else:
+                                acp = f.acpl_pool[ao + cell * 6: ao + cell * 6 + 6]
+                                tmp = 0.0
+                                for k in range(2):
+                                    e1, t1, n1t = int(acp[k * 3]), int(acp[k * 3 + 1]), int(acp[k * 3 + 2])
+                                    for a in range(n1t):
+                                        tmp += f.eth_pool[e1 + a * nth0 + r] * src[b0 + j1 * rs + t1 + a]
                             tmp *= half
-                            fa[F, :n0] += E[j1, :] * tmp
+                            if eo < 0:
+                                fa[F, j1] += wq[j1] * tmp
+                            else:
+                                E = f.exy_pool[eo: eo + n1 * n0].reshape(n1, n0)
+                                fa[F, :n0] += E[j1, :] * tmp
             wF = [f.th_wF[F, tp0 + th] for F in range(4)]
             for n in range(nn):
                 i, j = divmod(n, ny)
                 u0 = u[n, th]
                 v = 0.0
                 if terms & SCAT:
-                    v = -ms[n] * float(Gt[:, th] @ u[n, :])
+                    v = -ms[n] * float(G[th, :nt] @ u[n, :nt])
                 if terms & MASS:
                     v += mk[n] * wt * u0
                 if terms & ICONV:
