@@ -1,0 +1,184 @@
+"""CPU: the host-built device tables (FlatMesh, mortar pools, masks, slab layout)
+and the kernel's algorithm, checked without a GPU.
+
+``tests/emulate.py`` walks the SAME tables the CUDA kernel reads, in numpy; if
+these tests pass and a GPU parity test fails, the bug is in the kernel, not in
+the tables.  Index tables and masks are compared bit-exactly, floating point
+results against the reference-made golden vectors to 1e-12.
+"""
+import numpy as np
+import pytest
+
+import emulate as E
+from conftest import golden_cases, load_golden, rel_err
+
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module", params=golden_cases())
+def case(request):
+    from rt_b200.dg.flatmesh import FlatMesh
+    mesh, d, prob = load_golden(request.param)
+    flat = FlatMesh(mesh)
+    g_off, g_pool, coef = E.host_tables(flat, prob)
+    return request.param, mesh, d, prob, flat, (g_off, g_pool, coef)
+
+
+def _to_slab(flat, x):
+    xs = np.zeros(flat.n_slab)
+    xs[flat.slab_index_of_dof()] = x
+    return xs
+
+
+def test_global_dof_order_matches_reference_enumeration(case):
+    """Column / cell offsets follow sorted keys with (i, j, a), a fastest
+    (get_idxs.py:17-22, mass_matrix.py:54-74)."""
+    _, mesh, d, _, flat, _ = case
+    off, k = 0, 0
+    for ck in sorted(mesh.cols):
+        col = mesh.cols[ck]
+        assert flat.col_dof_off[k] == off
+        assert (flat.col_nx[k], flat.col_ny[k]) == tuple(col.ndofs)
+        for cell_key in sorted(col.cells):
+            off += col.ndofs[0] * col.ndofs[1] * col.cells[cell_key].ndofs[0]
+        k += 1
+    assert off == flat.n_dof == mesh.get_ndof() == d["x"].size
+
+
+def test_slab_layout_is_a_permutation_with_even_rows(case):
+    _, _, _, _, flat, _ = case
+    perm = flat.slab_index_of_dof()
+    assert np.unique(perm).size == flat.n_dof
+    assert perm.min() >= 0 and perm.max() < flat.n_slab
+    assert np.all(flat.col_slab_off % 2 == 0) and np.all(flat.sig_ntp % 2 == 0)
+    assert np.all((flat.sig_ntp - flat.sig_nt >= 0) & (flat.sig_ntp - flat.sig_nt <= 1))
+
+
+def test_interior_mask_bit_exact(case):
+    _, _, d, _, flat, _ = case
+    assert np.array_equal(flat.interior_mask_dof(), d["mask"])
+
+
+def test_neighbour_tables_match_mesh(case):
+    """Face tables point at the opposite face of the column Mesh.nhbr_keys names."""
+    _, mesh, _, _, flat, _ = case
+    keys = sorted(mesh.cols)
+    for c, ck in enumerate(keys):
+        col = mesh.cols[ck]
+        for F in range(4):
+            a, b = col.nhbr_keys[F]
+            want = [a] if (b is None or b == a) else [a, b]
+            want = [w for w in want if w is not None]
+            have = [s for s in range(2) if flat.face_base[c * 8 + F * 2 + s] != -1]
+            assert len(have) == len(want)
+            assert bool(flat.col_bdry[c] >> F & 1) == (len(want) == 0)
+            for s, wk in zip(have, want):
+                g = keys.index(wk)
+                base = int(flat.face_base[c * 8 + F * 2 + s])
+                assert flat.col_slab_off[g] <= base < flat.col_slab_off[g] + \
+                    flat.col_nx[g] * flat.col_ny[g] * flat.sig_ntp[flat.col_sig[g]]
+
+
+@pytest.mark.parametrize("terms,key,sign", [(3, "y_ms", 1.0), (4, "y_ic", -1.0),
+                                            (8, "y_bc", 1.0), (15, "y_a", 1.0)])
+def test_emulated_kernel_matches_reference_golden(case, terms, key, sign):
+    name, _, d, _, flat, tabs = case
+    perm = flat.slab_index_of_dof()
+    ys = E.apply_slab(flat, *tabs, _to_slab(flat, d["x"]), terms=terms)
+    err = rel_err(sign * ys[perm], d[key])
+    assert err <= TOL, "%s terms=%d: %.3e" % (name, terms, err)
+    pad = np.ones(flat.n_slab, bool)
+    pad[perm] = False
+    assert np.all(ys[pad] == 0.0)
+
+
+def test_emulated_interior_apply_and_rhs(case):
+    _, _, d, _, flat, tabs = case
+    perm, mask = flat.slab_index_of_dof(), d["mask"]
+    y = E.apply_slab(flat, *tabs, _to_slab(flat, d["x"] * mask), interior_only=True)[perm]
+    assert rel_err(y[mask], d["y_ii"]) <= TOL and np.all(y[~mask] == 0.0)
+    lift = E.apply_slab(flat, *tabs, _to_slab(flat, d["g_vec"] * ~mask), interior_only=True)[perm]
+    assert rel_err(d["f_vec"][mask] - lift[mask], d["rhs"]) <= TOL
+
+
+def test_general_mortar_path_equals_conforming_fast_path():
+    """The -1 ("conforming") flags are a pure shortcut: with them disabled the
+    general E^{x|y} / E^theta path gives the same numbers."""
+    from rt_b200.dg.flatmesh import FlatMesh
+    mesh, d, prob = load_golden("c1_uniform")
+    fast, slow = FlatMesh(mesh), FlatMesh(mesh, conforming_fast_path=False)
+    assert (fast.face_exy == -1).any() and not (slow.face_exy == -1).any()
+    x = _to_slab(fast, d["x"])
+    ya = E.apply_slab(fast, *E.host_tables(fast, prob), x, terms=8)
+    yb = E.apply_slab(slow, *E.host_tables(slow, prob), x, terms=8)
+    assert rel_err(ya, yb) <= 1e-14
+
+
+def test_uniform_generator_equals_mesh_builder():
+    """MeshArrays.uniform (the direct generator used for the 2.6e8-DoF benchmark
+    mesh) produces bit-identical tables to the Mesh-object path."""
+    from rt_b200 import configs
+    from rt_b200.dg.flatmesh import FlatMesh, MeshArrays
+    for pb in ([False, False], [True, False]):
+        mesh = configs.build_mesh([3.0, 2.0], pb, [4, 3, 5], nref_ang=3, nref_spt=2)
+        a = FlatMesh(MeshArrays.from_mesh(mesh))
+        b = FlatMesh(MeshArrays.uniform([3.0, 2.0], 2, 3, [4, 3, 5], pbcs=pb))
+        for name in ("col_nx", "col_ny", "col_sig", "col_bdry", "col_dof_off", "col_slab_off",
+                     "col_coef_off", "col_dx", "col_dy", "face_base", "face_rstride", "face_exy",
+                     "face_n1", "face_acpl", "sig_nt", "sig_ntp", "cell_nth", "cell_thoff",
+                     "th_wt", "th_ct", "th_st", "th_wF", "th_cell", "th_bits", "exy_pool",
+                     "eth_pool", "acpl_pool", "lgl_w", "lgl_s"):
+            assert np.array_equal(getattr(a, name), getattr(b, name)), name
+        assert np.array_equal(a.interior_mask_dof(), b.interior_mask_dof())
+
+
+def test_limits_are_enforced():
+    from rt_b200 import configs
+    from rt_b200.dg.flatmesh import FlatMesh, MAX_NXY
+    mesh = configs.build_mesh([1.0, 1.0], [False, False], [MAX_NXY + 1, 3, 3], nref_ang=2, nref_spt=0)
+    with pytest.raises(ValueError):
+        FlatMesh(mesh)
+
+
+# ---- column partition over ranks (the reference's np.array_split) ---------- #
+def _partitioned_apply(mesh, prob, x, nranks, terms=15, interior_only=False):
+    """Run the emulated kernel rank by rank with an explicit halo exchange that
+    follows each rank's plan (send_src / peer_* tables), like comm.cu does."""
+    from rt_b200.dg.flatmesh import FlatMesh
+    flats = [FlatMesh(mesh, rank=r, nranks=nranks) for r in range(nranks)]
+    xs = []
+    for f in flats:
+        loc = x[f.dof0:f.dof0 + f.n_dof]
+        s = np.zeros(f.n_slab)
+        s[f.slab_index_of_dof()] = loc
+        xs.append(s)
+    # pack on the sender, deliver into the needer's ghost buffer
+    ghosts = [np.full(max(f.n_ghost, 1), np.nan) for f in flats]
+    for r, f in enumerate(flats):
+        for pi, p in enumerate(f.peer_rank):
+            payload = xs[r][f.send_src[f.peer_send0[pi]:f.peer_send0[pi + 1]]]
+            fp = flats[p]
+            qi = list(fp.peer_rank).index(r)
+            lo, hi = fp.peer_recv0[qi], fp.peer_recv0[qi + 1]
+            assert hi - lo == payload.size
+            ghosts[p][lo:hi] = payload
+    out = np.zeros_like(x)
+    for r, f in enumerate(flats):
+        tabs = E.host_tables(f, prob)
+        ys = E.apply_slab(f, *tabs, xs[r], terms=terms, interior_only=interior_only,
+                          ghost=ghosts[r])
+        out[f.dof0:f.dof0 + f.n_dof] = ys[f.slab_index_of_dof()]
+    return out, flats
+
+
+@pytest.mark.parametrize("name", ["c1_uniform", "hp_mixed", "periodic_small"])
+@pytest.mark.parametrize("nranks", [2, 3, 8])
+def test_partitioned_apply_equals_single_rank(name, nranks):
+    mesh, d, prob = load_golden(name)
+    y, flats = _partitioned_apply(mesh, prob, d["x"], nranks)
+    assert rel_err(y, d["y_a"]) <= TOL
+    # ownership: the reference's contiguous split of the sorted key list
+    keys = np.array(sorted(mesh.cols))
+    for r, f in enumerate(flats):
+        assert np.array_equal(keys[f.col_global], np.array_split(keys, nranks)[r])
+    assert sum(f.n_dof for f in flats) == d["x"].size
