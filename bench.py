@@ -398,8 +398,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gmres", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--dense-scattering", action="store_true",
+                    help="force the dense (DMMA) scattering product even on uniform angular meshes")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.dense_scattering:
+        os.environ["RTB200_DENSE_SCATTERING"] = "1"
     if args.impl == "reference":
         run_reference(args)
     else:

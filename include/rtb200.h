@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define RTB200_ABI_VERSION 1
+#define RTB200_ABI_VERSION 2
 
 /* error codes */
 #define RTB200_OK            0
@@ -155,6 +155,20 @@ typedef struct rtb200_flatmesh {
     const int64_t* peer_send0;  /* [n_peer+1] ranges in send_src                 */
     const int64_t* peer_recv0;  /* [n_peer+1] ranges in the ghost buffer         */
     int64_t n_send;       const int64_t* send_src;  /* slab index of every double to send */
+
+    /* block-circulant scattering tables (optional; n_circ_pool = 0: none).
+       A signature whose cells all have the same width and order (NC cells of P
+       nodes) and whose G is block circulant in the cell index,
+       G[(K,r),(K',a)] = C[(K-K') mod NC][r][a] (any Phi(theta - theta')), may
+       carry the block spectrum of C: the kernels then apply the scattering
+       sum with FFTs over the cell index instead of the dense product.
+       sig_circ_off[s] < 0: signature s has no such table.  Layout of one table:
+       [NC/2][P][P] complex (re, im) doubles, slot 0 = (Chat[0], Chat[NC/2]) / NC,
+       slot k = Chat[k] / (2 NC)  (rt/tables.py:circulant_spectrum). */
+    const int32_t* sig_circ_nc;   /* [n_sig] NC (power of two, 4..64) or 0        */
+    const int32_t* sig_circ_p;    /* [n_sig] P                                    */
+    const int64_t* sig_circ_off;  /* [n_sig] even offset into circ_pool or -1     */
+    int64_t n_circ_pool;  const double*  circ_pool;
 } rtb200_flatmesh;
 
 typedef struct rtb200_gmres_params {

@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_NXY = 12
 MAX_NTH = 16
 
@@ -49,6 +49,8 @@ class FlatMeshC(C.Structure):
         ("n_peer", C.c_int32), ("peer_rank", _i32p), ("peer_send0", _i64p),
         ("peer_recv0", _i64p),
         ("n_send", C.c_int64), ("send_src", _i64p),
+        ("sig_circ_nc", _i32p), ("sig_circ_p", _i32p), ("sig_circ_off", _i64p),
+        ("n_circ_pool", C.c_int64), ("circ_pool", _f64p),
     ]
 
 

@@ -21,11 +21,15 @@
 #include "rtb200_internal.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <map>
 #include <tuple>
 
 __constant__ double c_w[(RT_MAXN + 1) * RT_MAXN];
 __constant__ double c_s[(RT_MAXN + 1) * RT_MAXN * RT_MAXN];
+
+#include "apply_common.cuh"
+#include "fft_real.cuh"
 
 // --------------------------------------------------------------------------- //
 // apply kernel
@@ -66,23 +70,7 @@ struct GroupTab {
     const int32_t* grp_cols;    // column indices
 };
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-}
-__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(d0), "+d"(d1)
-                 : "d"(a), "d"(b));
-}
-
-__device__ __forceinline__ bool dof_masked(int i, int j, int nx, int ny, int bdry, int bits) {
-    return ((i == nx - 1) && (bdry & 1) && (bits & 16)) || ((j == ny - 1) && (bdry & 2) && (bits & 32)) ||
-           ((i == 0) && (bdry & 4) && (bits & 64)) || ((j == 0) && (bdry & 8) && (bits & 128));
-}
+#include "apply_circ.cuh"
 
 template <int N>
 __global__ void __launch_bounds__(AP_THREADS, 2)
@@ -90,7 +78,6 @@ k_apply(DevMesh m, GroupTab gt, unsigned terms, int interior_only, const double*
         const double* __restrict__ ghost, double* __restrict__ y, int ntps) {
     extern __shared__ __align__(16) double u_s[];
     __shared__ int s_col[AP_MAXCG];
-    constexpr int NF = N > 0 ? N : RT_MAXN;
     constexpr int AP_MT = ap_mt(N);
 
     const int g = blockIdx.x;
@@ -128,127 +115,16 @@ k_apply(DevMesh m, GroupTab gt, unsigned terms, int interior_only, const double*
 
     // ---- phase 1: streaming terms, one thread per (column, theta) ------------ //
     if (terms & (RTB200_TERM_MASS | RTB200_TERM_ICONV | RTB200_TERM_BCONV)) {
-        const double* wx = c_w + nx * RT_MAXN;
-        const double* wy = c_w + ny * RT_MAXN;
-        const double* Sx = c_s + nx * RT_MAXN * RT_MAXN;
-        const double* Sy = c_s + ny * RT_MAXN * RT_MAXN;
         for (int item = threadIdx.x; item < cg_n * ntp; item += AP_THREADS) {
             const int cg = item / ntp, th = item - cg * ntp;
             const int c = s_col[cg];
-            const double* us = u_s + cg * nn * ntps;
-            double* yc = y + m.col_slab_off[c] + th;
             if (th >= nt) {
+                double* yc = y + m.col_slab_off[c] + th;
                 for (int n = 0; n < nn; ++n) yc[(int64_t)n * ntp] = 0.0;
                 continue;
             }
-            const double hdx = 0.5 * m.col_dx[c], hdy = 0.5 * m.col_dy[c];
-            const int bdry = m.col_bdry[c];
-            const double* __restrict__ mk = m.coef + m.col_coef_off[c];
-            const int bits = m.th_bits[tp0 + th];
-            const double wt = m.th_wt[tp0 + th];
-            const double ct = m.th_ct[tp0 + th];
-            const double st = m.th_st[tp0 + th];
-
-            double fa[4][NF];
-#pragma unroll
-            for (int F = 0; F < 4; ++F)
-#pragma unroll
-                for (int q = 0; q < NF; ++q) fa[F][q] = 0.0;
-
-            if (terms & RTB200_TERM_BCONV) {
-                const int cell = m.th_cell[tp0 + th];
-                const int r = (bits >> 8) & 0xff;
-                const int nth0 = m.cell_nth[m.sig_cell0[sg] + cell];
-#pragma unroll
-                for (int F = 0; F < 4; ++F) {
-                    if ((bits >> F) & 1) continue;       // outflow for this angle
-                    if ((bdry >> F) & 1) continue;       // inflow through the domain boundary
-                    const int n0 = (F & 1) ? nx : ny;
-                    const double half = (F & 1) ? hdx : hdy;
-                    const double* wq = (F & 1) ? wx : wy;
-                    const double wF = m.th_wF[F * m.n_theta_pool + tp0 + th];
-                    for (int slot = 0; slot < 2; ++slot) {
-                        const int fidx = c * 8 + F * 2 + slot;
-                        const int64_t base = m.face_base[fidx];
-                        if (base == -1) continue;
-                        const double* __restrict__ src = base >= 0 ? x + base : ghost + (-(base + 2));
-                        const int rs = m.face_rstride[fidx];
-                        const int eo = m.face_exy[fidx];
-                        const int ao = m.face_acpl[fidx];
-                        if (eo < 0 && ao < 0) {
-                            // conforming neighbour: E = diag(w), E_theta = diag(wF)
-                            const double f = half * wF;
-#pragma unroll
-                            for (int q = 0; q < NF; ++q)
-                                if (q < n0) fa[F][q] = f * wq[q] * src[(int64_t)q * rs + th];
-                            continue;
-                        }
-                        const int n1 = m.face_n1[fidx];
-                        for (int j1 = 0; j1 < n1; ++j1) {
-                            double tmp;
-                            if (ao < 0) {
-                                tmp = wF * src[(int64_t)j1 * rs + th];
-                            } else {
-                                const int32_t* __restrict__ acp = m.acpl_pool + ao + cell * 6;
-                                tmp = 0.0;
-                                for (int k = 0; k < 2; ++k) {
-                                    const int n1t = acp[k * 3 + 2];
-                                    if (n1t == 0) continue;
-                                    const double* __restrict__ eth = m.eth_pool + acp[k * 3] + r;
-                                    const double* __restrict__ tr = src + (int64_t)j1 * rs + acp[k * 3 + 1];
-                                    for (int a = 0; a < n1t; ++a) tmp = fma(eth[a * nth0], tr[a], tmp);
-                                }
-                            }
-                            tmp *= half;
-                            if (eo < 0) {
-#pragma unroll
-                                for (int q = 0; q < NF; ++q)
-                                    if (q == j1) fa[F][q] = fma(wq[q], tmp, fa[F][q]);
-                            } else {
-                                const double* __restrict__ E = m.exy_pool + eo;
-#pragma unroll
-                                for (int q = 0; q < NF; ++q)
-                                    if (q < n0) fa[F][q] = fma(E[j1 * n0 + q], tmp, fa[F][q]);
-                            }
-                        }
-                    }
-                }
-            }
-            const double wF0 = m.th_wF[0 * m.n_theta_pool + tp0 + th];
-            const double wF1 = m.th_wF[1 * m.n_theta_pool + tp0 + th];
-            const double wF2 = m.th_wF[2 * m.n_theta_pool + tp0 + th];
-            const double wF3 = m.th_wF[3 * m.n_theta_pool + tp0 + th];
-
-#pragma unroll
-            for (int i = 0; i < NF; ++i) {
-                if (i >= nx) break;
-#pragma unroll
-                for (int j = 0; j < NF; ++j) {
-                    if (j >= ny) break;
-                    const int n = i * ny + j;
-                    const double u0 = us[n * ntps + th];
-                    double v = 0.0;
-                    if (terms & RTB200_TERM_MASS) v = mk[n] * wt * u0;
-                    if (terms & RTB200_TERM_ICONV) {
-                        double sx = 0.0, sy = 0.0;
-#pragma unroll
-                        for (int k = 0; k < NF; ++k)
-                            if (k < nx) sx = fma(Sx[i * RT_MAXN + k], us[(k * ny + j) * ntps + th], sx);
-#pragma unroll
-                        for (int k = 0; k < NF; ++k)
-                            if (k < ny) sy = fma(Sy[j * RT_MAXN + k], us[(i * ny + k) * ntps + th], sy);
-                        v -= hdy * wy[j] * ct * sx + hdx * wx[i] * st * sy;
-                    }
-                    if (terms & RTB200_TERM_BCONV) {
-                        if (i == nx - 1) v += (bits & 1) ? hdy * wy[j] * wF0 * u0 : fa[0][j];
-                        if (j == ny - 1) v += (bits & 2) ? hdx * wx[i] * wF1 * u0 : fa[1][i];
-                        if (i == 0) v += (bits & 4) ? hdy * wy[j] * wF2 * u0 : fa[2][j];
-                        if (j == 0) v += (bits & 8) ? hdx * wx[i] * wF3 * u0 : fa[3][i];
-                    }
-                    const bool masked = interior_only && dof_masked(i, j, nx, ny, bdry, bits);
-                    yc[(int64_t)n * ntp] = masked ? 0.0 : v;
-                }
-            }
+            stream_column_theta<N>(m, c, th, nx, ny, sg, ntp, tp0, u_s + cg * nn * ntps, ntps,
+                                   nullptr, 0, terms, interior_only, x, ghost, y);
         }
     }
     if (!(terms & RTB200_TERM_SCAT)) return;
@@ -443,10 +319,59 @@ static int launch_bucket(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int i
     return RTB200_OK;
 }
 
+// (N, NC, P) combinations the block-circulant kernel is compiled for: the
+// benchmark mesh (5, 32, 5), the initial meshes of the reference's experiments
+// ((5, 8, 3) manufactured-solution, (3, 8, 4) one-weak / two-strong, input.json
+// mesh_params) and small cases for the parity tests.  Other uniform angular
+// meshes run the dense kernel.
+#define RT_CIRC_COMBOS(X) X(5, 32, 5) X(5, 8, 3) X(3, 8, 4) X(4, 16, 4) X(3, 8, 3) X(4, 4, 4)
+
+static bool circ_supported(int n, int nc, int p) {
+#define X(N_, NC_, P_) if (n == N_ && nc == NC_ && p == P_) return true;
+    RT_CIRC_COMBOS(X)
+#undef X
+    return false;
+}
+
+static int circ_cpb(int n, int nc, int p) {
+#define X(N_, NC_, P_) if (n == N_ && nc == NC_ && p == P_) return CircCfg<N_, NC_, P_>::CPB;
+    RT_CIRC_COMBOS(X)
+#undef X
+    return 1;
+}
+
+template <int N, int NC, int P>
+static int launch_circ(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int interior_only,
+                       const double* x, double* y, cudaStream_t st) {
+    using Cfg = CircCfg<N, NC, P>;
+    auto kern = k_apply_circ<N, NC, P>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaFuncSetAttribute(k_apply_circ, smem)");
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaFuncSetAttribute(k_apply_circ, carveout)");
+    GroupTab gt{b.grp_first_dev, b.grp_count_dev, b.cols_dev};
+    kern<<<b.n_groups, Cfg::THREADS, Cfg::SMEM, st>>>(ctx->dm, gt, terms, interior_only, x,
+                                                      ctx->ghost_dev, y, b.circ_tab_dev);
+    ctx->launches++;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return rt_cuda(ctx, e, "k_apply_circ launch");
+    return RTB200_OK;
+}
+
 int rt_launch_apply(rtb200_ctx* ctx, unsigned terms, int interior_only, const double* x,
                     double* y, cudaStream_t st) {
     for (const Bucket& b : ctx->buckets) {
-        int rc;
+        int rc = RTB200_EUNSUPPORTED;
+        if (b.circ_nc > 0) {
+#define X(N_, NC_, P_)                                                                  \
+    if (b.n == N_ && b.circ_nc == NC_ && b.circ_p == P_)                                \
+        rc = launch_circ<N_, NC_, P_>(ctx, b, terms, interior_only, x, y, st);
+            RT_CIRC_COMBOS(X)
+#undef X
+            if (rc) return rc;
+            continue;
+        }
         switch (b.n) {
             case 2: rc = launch_bucket<2>(ctx, b, terms, interior_only, x, y, st); break;
             case 3: rc = launch_bucket<3>(ctx, b, terms, interior_only, x, y, st); break;
@@ -467,9 +392,21 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
     RT_CUDA(ctx, cudaMemcpyToSymbol(c_w, m->lgl_w, sizeof(double) * (RT_MAXN + 1) * RT_MAXN));
     RT_CUDA(ctx, cudaMemcpyToSymbol(c_s, m->lgl_s,
                                     sizeof(double) * (RT_MAXN + 1) * RT_MAXN * RT_MAXN));
-    // Launch buckets by compile-time size N; inside a bucket, columns of the same
-    // class (nx, ny, signature) are packed into groups of up to CG columns that
-    // share G in the scattering GEMM; one launch uses one smem row stride.
+    {
+        double hc[32], hs[32];
+        for (int t = 0; t < 32; ++t) {
+            hc[t] = cos(2.0 * M_PI * t / 64.0);
+            hs[t] = sin(2.0 * M_PI * t / 64.0);
+        }
+        hc[16] = 0.0;                                       // exact quarter turn
+        RT_CUDA(ctx, cudaMemcpyToSymbol(c_fft_cos, hc, sizeof(hc)));
+        RT_CUDA(ctx, cudaMemcpyToSymbol(c_fft_sin, hs, sizeof(hs)));
+    }
+    // Launch buckets.  Columns of the same class (nx, ny, signature) are packed
+    // into groups that one thread block processes together (they share G).
+    //   dense buckets    : one per compile-time size N (0 = generic), DMMA scattering;
+    //   circulant buckets: one per (N, signature) whose angular mesh is uniform and
+    //                      whose (N, NC, P) is compiled: FFT scattering.
     struct Cls { int n, nx, ny, sig; bool operator<(const Cls& o) const {
         return std::tie(n, nx, ny, sig) < std::tie(o.n, o.nx, o.ny, o.sig); } };
     std::map<Cls, std::vector<int32_t>> by_cls;
@@ -478,33 +415,48 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
         const int n = (nx == ny && nx >= 2 && nx <= 8) ? nx : 0;
         by_cls[Cls{n, nx, ny, m->col_sig[c]}].push_back(c);
     }
-    std::map<int, std::vector<int32_t>> cols, first, count;
-    std::map<int, int> max_ntp;
-    std::map<int, size_t> rows_max;
+    struct Acc {
+        std::vector<int32_t> cols, first, count;
+        int max_ntp = 0;
+        size_t rows_max = 0;
+    };
+    // key: (n, -1) dense, (n, sig) circulant
+    std::map<std::pair<int, int>, Acc> acc;
     for (auto& kv : by_cls) {
         const Cls& k = kv.first;
         const int nn = k.nx * k.ny;
-        int cg = ap_cg(nn);
+        const bool circ = ctx->use_circ && m->sig_circ_off && m->sig_circ_off[k.sig] >= 0 && k.n > 0 &&
+                          circ_supported(k.n, m->sig_circ_nc[k.sig], m->sig_circ_p[k.sig]);
+        const int cg = circ ? circ_cpb(k.n, m->sig_circ_nc[k.sig], m->sig_circ_p[k.sig]) : ap_cg(nn);
+        Acc& a = acc[{k.n, circ ? k.sig : -1}];
         auto& v = kv.second;
         for (size_t i = 0; i < v.size(); i += cg) {
             const int cnt = (int)std::min<size_t>(cg, v.size() - i);
-            first[k.n].push_back((int32_t)cols[k.n].size());
-            count[k.n].push_back(cnt);
-            for (int t = 0; t < cnt; ++t) cols[k.n].push_back(v[i + t]);
-            rows_max[k.n] = std::max(rows_max[k.n], (size_t)((cnt * nn + 7) / 8) * 8);
+            a.first.push_back((int32_t)a.cols.size());
+            a.count.push_back(cnt);
+            for (int t = 0; t < cnt; ++t) a.cols.push_back(v[i + t]);
+            a.rows_max = std::max(a.rows_max, (size_t)((cnt * nn + 7) / 8) * 8);
         }
-        max_ntp[k.n] = std::max(max_ntp[k.n], m->sig_ntp[k.sig]);
+        a.max_ntp = std::max(a.max_ntp, m->sig_ntp[k.sig]);
     }
-    for (auto& kv : cols) {
+    for (auto& kv : acc) {
+        Acc& a = kv.second;
         Bucket b;
-        b.n = kv.first;
-        b.count = (int)kv.second.size();
-        b.n_groups = (int)first[b.n].size();
-        b.max_ntp = max_ntp[b.n];
-        b.ntps = ntps_for(b.max_ntp);
-        b.smem = sizeof(double) * rows_max[b.n] * (size_t)b.ntps;
-        if (b.smem > 227 * 1024)
-            return rt_fail(ctx, RTB200_EUNSUPPORTED, "a column slab exceeds 227 KB of shared memory");
+        b.n = kv.first.first;
+        b.count = (int)a.cols.size();
+        b.n_groups = (int)a.first.size();
+        b.max_ntp = a.max_ntp;
+        if (kv.first.second >= 0) {
+            const int sig = kv.first.second;
+            b.circ_nc = m->sig_circ_nc[sig];
+            b.circ_p = m->sig_circ_p[sig];
+            b.circ_tab_dev = ctx->circ_pool_dev + m->sig_circ_off[sig];
+        } else {
+            b.ntps = ntps_for(b.max_ntp);
+            b.smem = sizeof(double) * a.rows_max * (size_t)b.ntps;
+            if (b.smem > 227 * 1024)
+                return rt_fail(ctx, RTB200_EUNSUPPORTED, "a column slab exceeds 227 KB of shared memory");
+        }
         auto up = [&](const std::vector<int32_t>& h, int32_t** d) -> int {
             RT_CUDA(ctx, cudaMalloc((void**)d, sizeof(int32_t) * h.size()));
             ctx->allocs.push_back(*d);
@@ -512,9 +464,9 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
             return RTB200_OK;
         };
         int rc;
-        if ((rc = up(kv.second, &b.cols_dev))) return rc;
-        if ((rc = up(first[b.n], &b.grp_first_dev))) return rc;
-        if ((rc = up(count[b.n], &b.grp_count_dev))) return rc;
+        if ((rc = up(a.cols, &b.cols_dev))) return rc;
+        if ((rc = up(a.first, &b.grp_first_dev))) return rc;
+        if ((rc = up(a.count, &b.grp_count_dev))) return rc;
         ctx->buckets.push_back(b);
     }
     return RTB200_OK;

@@ -9,6 +9,7 @@
 #include "rtb200_internal.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 int rt_fail(rtb200_ctx* ctx, int code, const std::string& msg) {
@@ -137,6 +138,23 @@ extern "C" int rtb200_set_mesh(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
     UP(coef, m->n_coef);
     ctx->coef_dev = const_cast<double*>(ctx->dm.coef);
     ctx->n_coef = m->n_coef;
+    ctx->circ_pool_dev = nullptr;
+    if (m->n_circ_pool > 0) {
+        if (!m->sig_circ_off || !m->sig_circ_nc || !m->sig_circ_p)
+            return rt_fail(ctx, RTB200_EINVAL, "circulant pool without per-signature tables");
+        for (int s = 0; s < m->n_sig; ++s)
+            if (m->sig_circ_off[s] >= 0 &&
+                ((m->sig_circ_off[s] & 1) || m->sig_circ_nc[s] * m->sig_circ_p[s] != m->sig_nt[s] ||
+                 m->sig_circ_off[s] + (int64_t)m->sig_circ_nc[s] * m->sig_circ_p[s] * m->sig_circ_p[s] >
+                     m->n_circ_pool))
+                return rt_fail(ctx, RTB200_EINVAL, "inconsistent circulant table of a signature");
+        int rc = upload(ctx, m->circ_pool, m->n_circ_pool, &ctx->circ_pool_dev, "circ_pool");
+        if (rc) return rc;
+    }
+    {
+        const char* env = getenv("RTB200_DENSE_SCATTERING");
+        ctx->use_circ = !(env && env[0] == '1');
+    }
 
     // halo plan
     ctx->n_ghost = m->n_ghost;

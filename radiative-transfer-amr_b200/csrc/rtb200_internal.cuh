@@ -40,6 +40,9 @@ struct Bucket {
     int32_t* cols_dev = nullptr;        // column indices, group after group
     int32_t* grp_first_dev = nullptr;   // [n_groups] first entry in cols_dev
     int32_t* grp_count_dev = nullptr;   // [n_groups] columns in the group
+    // block-circulant scattering (uniform angular mesh): NC cells of P nodes; 0 = dense
+    int circ_nc = 0, circ_p = 0;
+    const double* circ_tab_dev = nullptr;
 };
 
 struct NcclApi;                // resolved with dlopen in comm.cu
@@ -53,6 +56,8 @@ struct rtb200_ctx {
     std::vector<Bucket> buckets;
     double* coef_dev = nullptr;
     int64_t n_coef = 0;
+    const double* circ_pool_dev = nullptr;
+    bool use_circ = true;          // RTB200_DENSE_SCATTERING=1 in the environment disables it
     int64_t launches = 0;
     int sm_count = 148;
 

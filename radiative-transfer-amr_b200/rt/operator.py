@@ -107,6 +107,31 @@ def build_g_pool(flat: FlatMesh, Phi):
     return np.array(offs, np.int64), np.concatenate(parts)
 
 
+def build_circ_pool(flat: FlatMesh, sig_g_off, g_pool):
+    """Per signature with a uniform angular mesh (all cells the same level and
+    order, 4..64 cells): the block spectrum of G when G is block circulant
+    (``tables.circulant_blocks`` / ``circulant_spectrum``).  Returns
+    (nc[n_sig], p[n_sig], off[n_sig] (-1: none), pool)."""
+    ncs, ps, offs, parts, n = [], [], [], [], 0
+    for si, s in enumerate(flat.arrays.sigs):
+        nc, p = len(s.keys), int(s.nth[0])
+        tab = None
+        if nc in (4, 8, 16, 32, 64) and np.all(s.nth == p) and np.all(s.lv == s.lv[0]):
+            k8 = 8 * ((s.nt + 7) // 8)
+            G = g_pool[sig_g_off[si]: sig_g_off[si] + k8 * k8].reshape(k8, k8)[:s.nt, :s.nt]
+            Cb = T.circulant_blocks(G, nc, p)
+            if Cb is not None:
+                tab = T.circulant_spectrum(Cb).reshape(-1)
+        if tab is None:
+            ncs.append(0); ps.append(0); offs.append(-1)
+        else:
+            ncs.append(nc); ps.append(p); offs.append(n)
+            parts.append(tab)
+            n += tab.size
+    pool = np.concatenate(parts) if parts else np.zeros(0)
+    return (np.array(ncs, np.int32), np.array(ps, np.int32), np.array(offs, np.int64), pool)
+
+
 class RTOperator:
     """Device-resident operator ``A = (BC - IC) + (M - S)`` for one mesh."""
 
@@ -126,6 +151,7 @@ class RTOperator:
         self.shape = (self.n, self.n)
         self.sig_g_off, self.g_pool = build_g_pool(flat, Phi)
         self.coef = sample_coefficients(flat, kappa, sigma)
+        self.circ = build_circ_pool(flat, self.sig_g_off, self.g_pool)
         self._keep = []
         self.ctx = C.c_void_p()
         L.check(self.lib, None, self.lib.rtb200_create(self.device.index or 0, C.byref(self.ctx)),
@@ -170,6 +196,11 @@ class RTOperator:
         put("peer_recv0", f.peer_recv0, np.int64, C.c_int64)
         m.n_send = int(f.send_src.size)
         put("send_src", f.send_src if f.send_src.size else np.zeros(1), np.int64, C.c_int64)
+        put("sig_circ_nc", self.circ[0], np.int32, C.c_int32)
+        put("sig_circ_p", self.circ[1], np.int32, C.c_int32)
+        put("sig_circ_off", self.circ[2], np.int64, C.c_int64)
+        m.n_circ_pool = int(self.circ[3].size)
+        put("circ_pool", self.circ[3] if self.circ[3].size else np.zeros(2), np.float64, C.c_double)
         self._call("rtb200_set_mesh", self.lib.rtb200_set_mesh(self.ctx, C.byref(m)))
         keep.clear()
 

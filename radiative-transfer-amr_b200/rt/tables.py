@@ -138,3 +138,52 @@ def _eval_phi(Phi, th_r: np.ndarray, th_a: np.ndarray) -> np.ndarray:
 def scattering_kernel(Phi, theta: np.ndarray, wt: np.ndarray) -> np.ndarray:
     """G[r, a] = wt_r * wt_a * Phi(theta_r, theta_a) over a column's angular nodes."""
     return (wt[:, None] * wt[None, :]) * _eval_phi(Phi, theta, theta)
+
+
+# --------------------------------------------------------------------------- #
+# block-circulant scattering (uniform angular meshes)
+# --------------------------------------------------------------------------- #
+def circulant_blocks(G: np.ndarray, nc: int, p: int, rtol: float = 1.0e-13):
+    """If ``G`` (NT x NT, NT = nc * p, cell-major angular index) is block
+    circulant in the cell index -- G[(K, r), (K', a)] = C[(K - K') mod nc][r, a],
+    true whenever all cells of a column have the same width and order and Phi
+    depends on theta - theta' only -- return C[nc, p, p], else None.
+
+    The test is numerical (Phi is a user callable): every block row must equal
+    the shifted first block column to ``rtol * max|G|``.
+    """
+    if nc * p != G.shape[0] or G.shape[0] != G.shape[1]:
+        return None
+    B = G.reshape(nc, p, nc, p).transpose(0, 2, 1, 3)          # [K, K', r, a]
+    C = B[:, 0]                                                # C[d] = block (d, 0)
+    K = np.arange(nc)
+    shifted = C[(K[:, None] - K[None, :]) % nc]                # [K, K', r, a]
+    if np.max(np.abs(B - shifted)) > rtol * max(np.max(np.abs(G)), 1e-300):
+        return None
+    return np.ascontiguousarray(C)
+
+
+def circulant_spectrum(C: np.ndarray) -> np.ndarray:
+    """Device table of the block-circulant scattering product.
+
+    With X[k] = sum_K x[K] exp(-2 pi i k K / nc) (per intra-cell index), the
+    product y = G x is Y[k] = Chat[k] X[k], Chat[k] = sum_d C[d] exp(-2 pi i k d / nc),
+    for k = 0 .. nc/2 (real data: Hermitian spectrum).  The kernel's transforms
+    are unnormalised: its forward pass returns X[0], X[nc/2] as they are and
+    2 X[k] for 0 < k < nc/2, its inverse pass returns nc * x.  The table folds
+    those factors in and packs the two real bins into slot 0:
+
+        T[0, r, a]  = (Chat[0][r, a], Chat[nc/2][r, a]) / nc          (both real)
+        T[k, r, a]  = Chat[k][r, a] / (2 nc),      0 < k < nc/2       (complex)
+
+    returned as float64[nc/2, p, p, 2] (re, im).
+    """
+    nc, p, _ = C.shape
+    Ch = np.fft.fft(C, axis=0)                                 # [k, r, a]
+    M = nc // 2
+    T = np.zeros((M, p, p, 2))
+    T[0, :, :, 0] = Ch[0].real / nc
+    T[0, :, :, 1] = Ch[M].real / nc
+    T[1:, :, :, 0] = Ch[1:M].real / (2.0 * nc)
+    T[1:, :, :, 1] = Ch[1:M].imag / (2.0 * nc)
+    return T

@@ -90,7 +90,10 @@ def build_cases():
             "c1_manufactured": (c1_uniform, "manufactured-solution"),
             "hp_mixed": (hp_mixed, "two-strong-scatterers"),
             "test_mesh_script": (test_mesh_script, "one-weak-scatterer"),
-            "periodic_small": (periodic_small, "one-weak-scatterer")}
+            "periodic_small": (periodic_small, "one-weak-scatterer"),
+            # same hp mesh with the smooth manufactured-solution coefficients: a
+            # non-trivial right-hand side that unpreconditioned GMRES can solve
+            "hp_manufactured": (hp_mixed, "manufactured-solution")}
 
 
 def problem_for(name, Ls):

@@ -28,7 +28,7 @@ UNPRECONDITIONED_OK = [c for c in golden_cases() if c not in ("hp_mixed", "test_
 def test_solve_matches_reference_solution(case, torch_cuda):
     mesh, d, prob = load_golden(case)
     uh, conv, minfo, uvec = prob.solve(mesh, ksp_type="gmres", pc_type="none", rtol=1e-13,
-                                       atol=0.0, max_it=3000, return_vector=True)
+                                       atol=0.0, max_it=8000, return_vector=True)
     assert conv["converged_reason"] > 0, conv["converged_reason"]
     assert len(conv["convergence_history"]) == conv["iteration_number"] + 1
     assert rel_err(uvec, d["u"]) <= SOL_TOL
@@ -50,13 +50,25 @@ def test_orthogonalisation_modes_agree(orth, torch_cuda):
 
 
 def test_reference_default_tolerances_report_reason(torch_cuda):
-    """With the reference's rtol = atol = 1e-15 the solve stops on ATOL/RTOL or
-    hits max_it; either way it is reported, not raised (solve.py:85-108)."""
+    """With the reference's rtol = atol = 1e-15 (solve.py:85-89) the outcome is
+    reported in converged_reason with PETSc's codes, never raised.
+
+    periodic_small: the beam boundary data of one-weak-scatterer is ~1e-84 on this
+    coarse angular mesh, so the initial residual is already below atol: ATOL (3)
+    at iteration 0, as KSPSolve would report.  c1_uniform with max_it = 120: the
+    iteration limit is hit first: ITS (-3)."""
     mesh, d, prob = load_golden("periodic_small")
     uh, conv, _ = prob.solve(mesh, max_it=400)
-    assert conv["converged_reason"] in (2, 3, -3)
-    assert conv["iteration_number"] <= 400
-    assert rel_err(uh.to_vector(), d["u"]) <= SOL_TOL
+    assert conv["converged_reason"] == 3 and conv["iteration_number"] == 0
+    assert len(conv["convergence_history"]) == 1
+    assert np.linalg.norm(uh.to_vector() - d["u"]) <= 1e-15
+
+    mesh, d, prob = load_golden("c1_uniform")
+    uh, conv, minfo = prob.solve(mesh, pc_type="none", max_it=120)
+    assert conv["converged_reason"] == -3 and conv["iteration_number"] == 120
+    h = np.array(conv["convergence_history"])
+    assert h.size == 121 and np.all(np.diff(h[:51]) <= 1e-300 + 1e-12 * h[:50])   # monotone within a cycle
+    assert conv["res_best"] == h.min() and conv["res_f"] == h[-1]
 
 
 def test_manufactured_solution_accuracy(torch_cuda):

@@ -132,6 +132,39 @@ def test_uniform_generator_equals_mesh_builder():
         assert np.array_equal(a.interior_mask_dof(), b.interior_mask_dof())
 
 
+@pytest.mark.parametrize("nc,p", [(4, 4), (8, 3), (16, 4), (32, 5), (64, 2)])
+def test_block_circulant_tables_reproduce_dense_scattering(nc, p):
+    """rt/tables.py:circulant_blocks / circulant_spectrum against the dense G:
+    rfft over the cell index, block product per frequency with the device table
+    (its packing and scale factors), inverse -- the kernel's algorithm in numpy."""
+    from rt_b200 import configs
+    from rt_b200.rt import tables as T
+    te = np.linspace(0.0, 2 * np.pi, nc + 1)
+    theta, wt = T.angular_nodes(zip(te[:-1], te[1:], [p] * nc))
+    for prob in (configs.two_strong_scatterers(), configs.manufactured_solution()[0]):
+        G = T.scattering_kernel(prob.Phi, theta, wt)
+        C = T.circulant_blocks(G, nc, p)
+        assert C is not None
+        tab = T.circulant_spectrum(C)
+        assert tab.shape == (nc // 2, p, p, 2)
+        u = np.random.default_rng(2).standard_normal((nc, p))
+        X = np.fft.rfft(u, axis=0)                                   # [nc/2+1, p]
+        M = nc // 2
+        slots = np.concatenate([[X[0].real + 1j * X[M].real], 2.0 * X[1:M]])   # kernel forward pass
+        Y = np.zeros((M, p), complex)
+        Y[0] = tab[0, :, :, 0] @ slots[0].real + 1j * (tab[0, :, :, 1] @ slots[0].imag)
+        for k in range(1, M):
+            Y[k] = (tab[k, :, :, 0] + 1j * tab[k, :, :, 1]) @ slots[k]
+        spec = np.concatenate([[Y[0].real], Y[1:], [Y[0].imag]])     # true spectrum / nc
+        y = np.fft.irfft(spec, n=nc, axis=0) * nc                    # kernel inverse returns nc * x
+        ref = (G @ u.reshape(-1)).reshape(nc, p)
+        assert rel_err(y, ref) <= 1e-13
+    # not circulant: non-uniform weights or a Phi that is not a function of the difference
+    assert T.circulant_blocks(G * (1 + 1e-9 * np.arange(nc * p))[:, None], nc, p) is None
+    Phi_bad = lambda a, b: 1.0 + 0.1 * np.cos(a) * np.cos(2 * b)     # noqa: E731
+    assert T.circulant_blocks(T.scattering_kernel(Phi_bad, theta, wt), nc, p) is None
+
+
 def test_limits_are_enforced():
     from rt_b200 import configs
     from rt_b200.dg.flatmesh import FlatMesh, MAX_NXY
