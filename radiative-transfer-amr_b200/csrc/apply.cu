@@ -333,13 +333,6 @@ static bool circ_supported(int n, int nc, int p) {
     return false;
 }
 
-static int circ_cpb(int n, int nc, int p) {
-#define X(N_, NC_, P_) if (n == N_ && nc == NC_ && p == P_) return CircCfg<N_, NC_, P_>::CPB;
-    RT_CIRC_COMBOS(X)
-#undef X
-    return 1;
-}
-
 template <int N, int NC, int P>
 static int launch_circ(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int interior_only,
                        const double* x, double* y, cudaStream_t st) {
@@ -350,9 +343,9 @@ static int launch_circ(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int int
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaFuncSetAttribute(k_apply_circ, carveout)");
-    GroupTab gt{b.grp_first_dev, b.grp_count_dev, b.cols_dev};
-    kern<<<b.n_groups, Cfg::THREADS, Cfg::SMEM, st>>>(ctx->dm, gt, terms, interior_only, x,
-                                                      ctx->ghost_dev, y, b.circ_tab_dev);
+    kern<<<b.count, Cfg::THREADS, Cfg::SMEM, st>>>(ctx->dm, b.cols_dev, b.circ_sig, terms,
+                                                   interior_only, x, ctx->ghost_dev, y,
+                                                   b.circ_tab_dev);
     ctx->launches++;
     e = cudaGetLastError();
     if (e != cudaSuccess) return rt_cuda(ctx, e, "k_apply_circ launch");
@@ -427,7 +420,7 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
         const int nn = k.nx * k.ny;
         const bool circ = ctx->use_circ && m->sig_circ_off && m->sig_circ_off[k.sig] >= 0 && k.n > 0 &&
                           circ_supported(k.n, m->sig_circ_nc[k.sig], m->sig_circ_p[k.sig]);
-        const int cg = circ ? circ_cpb(k.n, m->sig_circ_nc[k.sig], m->sig_circ_p[k.sig]) : ap_cg(nn);
+        const int cg = circ ? 1 : ap_cg(nn);
         Acc& a = acc[{k.n, circ ? k.sig : -1}];
         auto& v = kv.second;
         for (size_t i = 0; i < v.size(); i += cg) {
@@ -450,6 +443,7 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
             const int sig = kv.first.second;
             b.circ_nc = m->sig_circ_nc[sig];
             b.circ_p = m->sig_circ_p[sig];
+            b.circ_sig = sig;
             b.circ_tab_dev = ctx->circ_pool_dev + m->sig_circ_off[sig];
         } else {
             b.ntps = ntps_for(b.max_ntp);

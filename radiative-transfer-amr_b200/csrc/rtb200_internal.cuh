@@ -41,7 +41,7 @@ struct Bucket {
     int32_t* grp_first_dev = nullptr;   // [n_groups] first entry in cols_dev
     int32_t* grp_count_dev = nullptr;   // [n_groups] columns in the group
     // block-circulant scattering (uniform angular mesh): NC cells of P nodes; 0 = dense
-    int circ_nc = 0, circ_p = 0;
+    int circ_nc = 0, circ_p = 0, circ_sig = 0;
     const double* circ_tab_dev = nullptr;
 };
 
