@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <map>
 #include <tuple>
 
@@ -71,6 +72,7 @@ struct GroupTab {
 };
 
 #include "apply_circ.cuh"
+#include "apply_circ7.cuh"
 
 template <int N>
 __global__ void __launch_bounds__(AP_THREADS, 2)
@@ -336,9 +338,33 @@ static bool circ_supported(int n, int nc, int p) {
 template <int N, int NC, int P>
 static int launch_circ(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int interior_only,
                        const double* x, double* y, cudaStream_t st) {
+    cudaError_t e;
+    if constexpr (NC >= 8) {
+        // persistent, prefetching kernel (apply_circ7.cuh): 2 blocks per SM walk the column list
+        if (ctx->circ_version >= 7 && b.circ_conforming) {
+            using Cfg = Circ7Cfg<N, NC, P>;
+            auto kern = k_apply_circ7<N, NC, P>;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+            if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaFuncSetAttribute(k_apply_circ7, smem)");
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaFuncSetAttribute(k_apply_circ7, carveout)");
+            const int grid = std::min(b.count, 2 * ctx->sm_count);
+            if (b.circ_tab_host.size() != sizeof(CircTab7<Cfg>) / sizeof(double))
+                return rt_fail(ctx, RTB200_EINVAL, "circulant table size mismatch");
+            CircTab7<Cfg> T;                      // 16 M P^2 bytes, passed in the constant bank
+            memcpy(&T, b.circ_tab_host.data(), sizeof(T));
+            kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(ctx->dm, b.cols_dev, b.count, b.circ_sig, terms,
+                                                        interior_only, x, ctx->ghost_dev, y, T);
+            ctx->launches++;
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return rt_cuda(ctx, e, "k_apply_circ7 launch");
+            return RTB200_OK;
+        }
+    }
     using Cfg = CircCfg<N, NC, P>;
     auto kern = k_apply_circ<N, NC, P>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaFuncSetAttribute(k_apply_circ, smem)");
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
@@ -413,16 +439,36 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
         int max_ntp = 0;
         size_t rows_max = 0;
     };
-    // key: (n, -1) dense, (n, sig) circulant
-    std::map<std::pair<int, int>, Acc> acc;
+    // key: (n, -1, 0) dense, (n, sig, mortar?) circulant.  Circulant columns whose faces are
+    // all conforming (no hanging node, p- or angular mismatch) go to the persistent kernel
+    // (apply_circ7.cuh, no mortar code at all); the others to k_apply_circ.
+    auto has_mortar = [&](int c) {
+        for (int F = 0; F < 4; ++F) {
+            const int f = c * 8 + 2 * F;
+            if (m->face_base[f + 1] != -1) return true;
+            if (m->face_base[f] != -1 && (m->face_exy[f] >= 0 || m->face_acpl[f] >= 0)) return true;
+        }
+        return false;
+    };
+    std::map<std::tuple<int, int, int>, Acc> acc;
     for (auto& kv : by_cls) {
         const Cls& k = kv.first;
         const int nn = k.nx * k.ny;
         const bool circ = ctx->use_circ && m->sig_circ_off && m->sig_circ_off[k.sig] >= 0 && k.n > 0 &&
                           circ_supported(k.n, m->sig_circ_nc[k.sig], m->sig_circ_p[k.sig]);
         const int cg = circ ? 1 : ap_cg(nn);
-        Acc& a = acc[{k.n, circ ? k.sig : -1}];
         auto& v = kv.second;
+        if (circ) {
+            for (int c : v) {
+                Acc& a = acc[{k.n, k.sig, has_mortar(c) ? 1 : 0}];
+                a.first.push_back((int32_t)a.cols.size());
+                a.count.push_back(1);
+                a.cols.push_back(c);
+                a.max_ntp = std::max(a.max_ntp, m->sig_ntp[k.sig]);
+            }
+            continue;
+        }
+        Acc& a = acc[{k.n, -1, 0}];
         for (size_t i = 0; i < v.size(); i += cg) {
             const int cnt = (int)std::min<size_t>(cg, v.size() - i);
             a.first.push_back((int32_t)a.cols.size());
@@ -435,16 +481,19 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
     for (auto& kv : acc) {
         Acc& a = kv.second;
         Bucket b;
-        b.n = kv.first.first;
+        b.n = std::get<0>(kv.first);
         b.count = (int)a.cols.size();
         b.n_groups = (int)a.first.size();
         b.max_ntp = a.max_ntp;
-        if (kv.first.second >= 0) {
-            const int sig = kv.first.second;
+        if (std::get<1>(kv.first) >= 0) {
+            const int sig = std::get<1>(kv.first);
+            b.circ_conforming = std::get<2>(kv.first) == 0;
             b.circ_nc = m->sig_circ_nc[sig];
             b.circ_p = m->sig_circ_p[sig];
             b.circ_sig = sig;
             b.circ_tab_dev = ctx->circ_pool_dev + m->sig_circ_off[sig];
+            const double* th = m->circ_pool + m->sig_circ_off[sig];
+            b.circ_tab_host.assign(th, th + (size_t)(b.circ_nc / 2) * b.circ_p * b.circ_p * 2);
         } else {
             b.ntps = ntps_for(b.max_ntp);
             b.smem = sizeof(double) * a.rows_max * (size_t)b.ntps;

@@ -1,0 +1,521 @@
+// Persistent, prefetching apply kernel for columns with a UNIFORM angular mesh
+// (NC >= 8 equal cells of P nodes; block-circulant scattering, see apply_circ.cuh
+// for the algorithm and the table conventions).
+//
+// What changed against k_apply_circ (one block per column, phases in lock step):
+//   * persistent blocks (2 per SM) walk the column list with a grid stride and
+//     PREFETCH the next column's slab + coefficients with cp.async into a second
+//     buffer while the current column is being processed: the HBM stream and the
+//     FP64 phases overlap by construction instead of by luck of block scheduling;
+//   * twice the threads per column at <= 96 registers: every length-NC real FFT is
+//     split over the two lanes (l, l ^ 16) of a warp -- each transforms the even or
+//     the odd samples (length NC/2, in registers), the last radix-2 stage swaps NC/4
+//     doubles with shuffles -- and the streaming terms of an angle are split over
+//     two threads (first / second half of the spatial nodes);
+//   * block product: a 5-lane group owns one (frequency slot, node) item at a time
+//     and walks a contiguous, evenly sized range of the NC/2 x NN items, next
+//     item's operands in flight while the current one is multiplied (4 chains);
+//   * the per-angle tables (weights, cos, sin, face weights, upwind bits) are
+//     staged in shared memory once per block; column metadata runs two columns
+//     ahead in a 3-slot ring.
+//
+// Shared memory per block at (N, NC, P) = (5, 32, 5): 2 x 33.0 KB (U) + 34.0 KB (W)
+// + 6.4 KB (block spectrum) + 4.5 KB (angle tables) + 0.8 KB = 111.7 KB -> 2 blocks / SM.
+#pragma once
+#ifndef RT7_MINB
+#define RT7_MINB 2
+#endif
+
+template <int N_, int NC_, int P_>
+struct Circ7Cfg {
+    static constexpr int N = N_, NC = NC_, P = P_;
+    static constexpr int NN = N * N, NT = NC * P, M = NC / 2, H = NC / 2, Q = NC / 4;
+    static constexpr int NTP = NT + (NT & 1);
+    static constexpr int NPW = 16 / P;                         // nodes a warp can transform (2 lanes / sequence)
+    static constexpr int SC_WARPS = (NN + NPW - 1) / NPW;
+    static constexpr int NTW = (NT + 31) / 32 * 32;            // S role: threads per half
+    static constexpr int THREADS = SC_WARPS * 32 > 2 * NTW ? SC_WARPS * 32 : 2 * NTW;
+    static constexpr int NWARPS = THREADS / 32;
+    static constexpr int NW_MAX = (NN + NWARPS - 1) / NWARPS;  // nodes per warp (even split)
+    static constexpr int SU = CircCfg<N_, NC_, P_>::SU, SW = CircCfg<N_, NC_, P_>::SW;
+    static constexpr int U_DOUBLES = (NN * SU + 1) & ~1;
+    static constexpr int W_DOUBLES = NN * SW;
+    static constexpr int T_DOUBLES = M * P * P * 2;            // block spectrum (double2 [M][P][P])
+    static constexpr int TAB_DOUBLES = 3 * NT + (NT + 1) / 2;  // wt, wt cos, wt sin + int bits
+    static constexpr int COEF_DOUBLES = 2 * NN;
+    static constexpr size_t SMEM = sizeof(double) * (size_t)(2 * U_DOUBLES + W_DOUBLES + T_DOUBLES +
+                                                             TAB_DOUBLES + 2 * COEF_DOUBLES);
+    static constexpr int NA = (NN + 1) / 2;                    // nodes [0, NA) -> half 0, rest -> half 1
+    static_assert(NW_MAX * P <= 16, "a warp transforms at most 16 sequences");
+};
+
+struct ColMeta7 {
+    ColMeta cm;
+    long long coef_off;
+};
+
+__device__ __forceinline__ void load_col_meta7(const DevMesh& m, const int c, ColMeta7& cm, const int t) {
+    load_col_meta(m, c, cm.cm, t);
+    if (t == 8) cm.coef_off = m.col_coef_off[c];
+}
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// ---- split real FFT: forward ------------------------------------------------ //
+// xs[m] = x[2 m + t], m < NC/2.  Output: the NC/4 spectrum slots this lane owns, in
+// the slot convention of fft_real.cuh for length NC (slot 0 = (X[0], X[NC/2]),
+// slot k = 2 X[k]):
+//   pair p (0 .. NC/8): k = 2 p + t ->  oa[p] = slot k,  ob[p] = slot NC/2 - k,
+//   except (t, p) = (0, 0):             oa[0] = slot 0,  ob[0] = slot NC/4.
+// With E / O the half-length spectra of the even / odd samples and w = exp(-2 pi i / NC):
+//   X[k] = E[k] + w^k O[k],  X[NC/2 - k] = conj(E[k] - w^k O[k]).
+template <int NC>
+__device__ __forceinline__ void split_forward(const double (&xs)[NC / 2], const int t,
+                                              double2 (&oa)[NC / 8], double2 (&ob)[NC / 8]) {
+    constexpr int Q = NC / 4, NP = NC / 8;
+    double hr[Q], hi[Q];
+    rtfft::Real<NC / 2>::forward(xs, hr, hi);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        // lane t = 0 (even samples, E) sends E[2p+1]; lane t = 1 (O) sends O[2p]
+        const double sr = t ? hr[2 * p] : hr[2 * p + 1];
+        const double si = t ? hi[2 * p] : hi[2 * p + 1];
+        const double rr = __shfl_xor_sync(0xffffffffu, sr, 16);
+        const double ri = __shfl_xor_sync(0xffffffffu, si, 16);
+        // generic combination at k = 2p + t
+        const double er = t ? rr : hr[2 * p], ei = t ? ri : hi[2 * p];
+        const double orr = t ? hr[2 * p + 1] : rr, oi = t ? hi[2 * p + 1] : ri;
+        const double c = t ? c_fft_cos[(2 * p + 1) * (64 / NC)] : c_fft_cos[(2 * p) * (64 / NC)];
+        const double s = t ? c_fft_sin[(2 * p + 1) * (64 / NC)] : c_fft_sin[(2 * p) * (64 / NC)];
+        const double wr = fma(c, orr, s * oi), wi = fma(c, oi, -(s * orr));
+        double2 a = make_double2(er + wr, ei + wi);
+        double2 b = make_double2(er - wr, wi - ei);
+        if (p == 0) {
+            // t = 0: E = (E[0], E[Q]) and O = (O[0], O[Q]) are the packed real bins
+            const double2 sa = make_double2(hr[0] + rr, hr[0] - rr);
+            const double2 sb = make_double2(2.0 * hi[0], -2.0 * ri);
+            a = t ? a : sa;
+            b = t ? b : sb;
+        }
+        oa[p] = a;
+        ob[p] = b;
+    }
+}
+
+// ---- split real FFT: inverse ------------------------------------------------ //
+// ia / ib: the slots this lane owns (same ownership as split_forward), holding the
+// TRUE spectrum Y.  Output xs[m] = NC * x[2 m + t].
+//   A[k] = Y[k] + conj(Y[NC/2 - k])           -> even samples
+//   B[k] = (Y[k] - conj(Y[NC/2 - k])) w^{-k}  -> odd samples
+template <int NC>
+__device__ __forceinline__ void split_inverse(const double2 (&ia)[NC / 8], const double2 (&ib)[NC / 8],
+                                              const int t, double (&xs)[NC / 2]) {
+    constexpr int Q = NC / 4, NP = NC / 8;
+    double hr[Q], hi[Q];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const double2 yk = ia[p], ym = ib[p];
+        double ar = yk.x + ym.x, ai = yk.y - ym.y;
+        const double dr = yk.x - ym.x, di = yk.y + ym.y;
+        const double c = t ? c_fft_cos[(2 * p + 1) * (64 / NC)] : c_fft_cos[(2 * p) * (64 / NC)];
+        const double s = t ? c_fft_sin[(2 * p + 1) * (64 / NC)] : c_fft_sin[(2 * p) * (64 / NC)];
+        double br = fma(dr, c, -(di * s)), bi = fma(dr, s, di * c);
+        if (p == 0) {
+            // t = 0: yk = (Y[0], Y[NC/2]), ym = Y[NC/4]
+            const double a0 = yk.x + yk.y, aq = 2.0 * ym.x;
+            const double b0 = yk.x - yk.y, bq = -2.0 * ym.y;
+            ar = t ? ar : a0;
+            ai = t ? ai : aq;
+            br = t ? br : b0;
+            bi = t ? bi : bq;
+        }
+        // lane 0 keeps A and sends B[2p]; lane 1 keeps B and sends A[2p+1]
+        const double sr = t ? ar : br, si = t ? ai : bi;
+        const double rr = __shfl_xor_sync(0xffffffffu, sr, 16);
+        const double ri = __shfl_xor_sync(0xffffffffu, si, 16);
+        hr[2 * p] = t ? rr : ar;
+        hi[2 * p] = t ? ri : ai;
+        hr[2 * p + 1] = t ? br : rr;
+        hi[2 * p + 1] = t ? bi : ri;
+    }
+    rtfft::Real<NC / 2>::inverse(hr, hi, xs);
+}
+
+// ---- streaming terms of one angle, one half of the spatial nodes ------------- //
+// Same arithmetic as stream_theta_circ (apply_circ.cuh) for columns whose faces are all
+// conforming (the host routes columns with mortar faces to k_apply_circ); HALF = 0 owns nodes
+// [0, NA), HALF = 1 owns [NA, NN).  Row 0 always belongs to half 0 and row N-1 to
+// half 1, so the inflow x-face is handled by exactly one of the two threads.
+// FULL: all four terms (the solver's call); the term tests are compiled out.
+// Order: neighbour-trace loads are issued first and consumed last (L2 latency hidden
+// behind the two derivative passes over shared memory).
+template <int N, int HALF, bool FULL, typename Cfg>
+__device__ __noinline__ void stream7(
+    const ColMeta& cm, const double* __restrict__ coef_s, const double* __restrict__ tab,
+    const int th, const double* __restrict__ us, const double* __restrict__ ws, const unsigned terms,
+    const int interior_only, const double* __restrict__ x, const double* __restrict__ ghost,
+    double* __restrict__ y) {
+    constexpr int NN = N * N, NT = Cfg::NT, SU = Cfg::SU, SW = Cfg::SW, NTP = Cfg::NTP;
+    constexpr int NA = Cfg::NA;
+#define RT_MINE(i, j) (HALF == 0 ? ((i) * N + (j) < NA) : ((i) * N + (j) >= NA))
+    const double* wq = c_w + N * RT_MAXN;
+    const double* S = c_s + N * RT_MAXN * RT_MAXN;
+    const bool t_mass = FULL || (terms & RTB200_TERM_MASS), t_ic = FULL || (terms & RTB200_TERM_ICONV);
+    const bool t_bc = FULL || (terms & RTB200_TERM_BCONV);
+    const bool t_sc = FULL || ws != nullptr;
+
+    const int bits = reinterpret_cast<const int*>(tab + 3 * NT)[th];
+    const int Fx = (bits & 1) ? 2 : 0, Fy = (bits & 2) ? 3 : 1;        // the two inflow faces
+    const int bdry = cm.bdry;
+
+    // inflow x-face: row N-1 when Fx == 0 (half 1), row 0 when Fx == 2 (half 0)
+    constexpr int IX = HALF == 0 ? 0 : N - 1;
+    const bool own_x = (HALF == 0) == (Fx == 2);
+    const bool in_x = t_bc && own_x && !((bdry >> Fx) & 1);
+    const bool in_y = t_bc && !((bdry >> Fy) & 1);
+    double tx[N], ty[N];
+    {
+        const long long base = cm.face_base[2 * Fx];
+        const double* __restrict__ src = (base >= 0 ? x + base : ghost + (-(base + 2))) + th;
+        const int rs = cm.rs[2 * Fx];
+#pragma unroll
+        for (int q = 0; q < N; ++q) tx[q] = in_x ? src[(int64_t)q * rs] : 0.0;
+    }
+    {
+        const long long base = cm.face_base[2 * Fy];
+        const double* __restrict__ src = (base >= 0 ? x + base : ghost + (-(base + 2))) + th;
+        const int rs = cm.rs[2 * Fy];
+#pragma unroll
+        for (int q = 0; q < N; ++q)
+            ty[q] = (in_y && (RT_MINE(q, 0) || RT_MINE(q, N - 1))) ? src[(int64_t)q * rs] : 0.0;
+    }
+
+    // face weights wt cos(theta - F pi/2) = (ct, st, -ct, -st) for F = 0..3 (the table th_wF
+    // holds the same numbers up to the rounding of the shifted cosine)
+    const double wt = tab[th], ct = tab[NT + th], st = tab[2 * NT + th];
+    const double wF_inx = Fx == 0 ? ct : -ct, wF_iny = Fy == 1 ? st : -st;
+    const double hdx = cm.hdx, hdy = cm.hdy;
+    const double* __restrict__ ut = us + th;
+    double v[N][N];
+
+    // ---- pass Y: rows of u: y-derivative, mass, outflow faces -------------------- //
+    {
+        const double cout_x = t_bc ? -(hdy * wF_inx) : 0.0;   // the outflow x-face is Fx ^ 2
+        const double cout_y = t_bc ? -(hdx * wF_iny) : 0.0;
+        const bool out_lo_x = Fx == 0, out_lo_y = Fy == 1;    // outflow through face 2 (i = 0) / face 3 (j = 0)
+        const double mw = t_mass ? wt : 0.0;
+        const double hst = t_ic ? -(hdx * st) : 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (!(RT_MINE(i, 0) || RT_MINE(i, N - 1))) continue;
+            double row[N];
+#pragma unroll
+            for (int k = 0; k < N; ++k) row[k] = ut[(i * N + k) * SU];
+            const double cxi = hst * wq[i];
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                if (!RT_MINE(i, j)) continue;
+                const int n = i * N + j;
+                double s = S[j * RT_MAXN] * row[0];
+#pragma unroll
+                for (int k = 1; k < N; ++k) s = fma(S[j * RT_MAXN + k], row[k], s);
+                double acc = cxi * s;
+                acc = fma(coef_s[n] * mw, row[j], acc);
+                if (i == 0 && out_lo_x) acc = fma(cout_x * wq[j], row[j], acc);
+                if (i == N - 1 && !out_lo_x) acc = fma(cout_x * wq[j], row[j], acc);
+                if (j == 0 && out_lo_y) acc = fma(cout_y * wq[i], row[j], acc);
+                if (j == N - 1 && !out_lo_y) acc = fma(cout_y * wq[i], row[j], acc);
+                v[i][j] = acc;
+            }
+        }
+    }
+
+    // ---- pass X: v[i][j] -= (dy/2) w_j ct sum_k S[i][k] u[k][j] ------------------ //
+    if (t_ic) {
+        const double hct = -(hdy * ct);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double col[N];
+#pragma unroll
+            for (int k = 0; k < N; ++k) col[k] = ut[(k * N + j) * SU];
+            const double cyj = hct * wq[j];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                if (!RT_MINE(i, j)) continue;
+                double s = S[i * RT_MAXN] * col[0];
+#pragma unroll
+                for (int k = 1; k < N; ++k) s = fma(S[i * RT_MAXN + k], col[k], s);
+                v[i][j] = fma(cyj, s, v[i][j]);
+            }
+        }
+    }
+
+    // ---- inflow faces (conforming neighbours: raw traces) -------------------------- //
+    if (t_bc) {
+        const double cin_x = hdy * wF_inx, cin_y = hdx * wF_iny;
+        if (own_x) {
+#pragma unroll
+            for (int q = 0; q < N; ++q) v[IX][q] = fma(cin_x * wq[q], tx[q], v[IX][q]);
+        }
+        if (Fy == 1) {
+#pragma unroll
+            for (int q = 0; q < N; ++q)
+                if (RT_MINE(q, N - 1)) v[q][N - 1] = fma(cin_y * wq[q], ty[q], v[q][N - 1]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < N; ++q)
+                if (RT_MINE(q, 0)) v[q][0] = fma(cin_y * wq[q], ty[q], v[q][0]);
+        }
+    }
+
+    // ---- scattering combine, interior restriction (get_masks.py:80-110), store ----- //
+    const bool msk = interior_only != 0;
+    const bool m0 = msk && (bdry & 1) && (bits & 16), m1 = msk && (bdry & 2) && (bits & 32);
+    const bool m2 = msk && (bdry & 4) && (bits & 64), m3 = msk && (bdry & 8) && (bits & 128);
+    double* yc = y + cm.slab_off + th;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            if (!RT_MINE(i, j)) continue;
+            const int n = i * N + j;
+            double acc = v[i][j];
+            if (t_sc) acc = fma(-coef_s[NN + n], ws[n * SW], acc);
+            bool masked = false;
+            if (i == N - 1) masked = masked || m0;
+            if (j == N - 1) masked = masked || m1;
+            if (i == 0) masked = masked || m2;
+            if (j == 0) masked = masked || m3;
+            yc[(int64_t)n * NTP] = masked ? 0.0 : acc;
+        }
+    }
+#undef RT_MINE
+}
+
+// ---- scattering, per column: F (FFT) | M (block product) | I (inverse FFT) --------- //
+// F / I: a warp owns whole spatial nodes (an even split of the NN nodes over the warps,
+//        at most 16 / P each); lanes l and l ^ 16 share one sequence (node, a).
+//        F: U -> spectrum slots in W;  I: slots -> real row W[node][theta], in place
+//        (only the owning warp touches a node's row: __syncwarp is enough).
+// M:     lane = spatial node, the frequency slot k is warp-uniform: the P x P complex
+//        block T[k] is read from shared memory with warp-uniform (broadcast, one
+//        wavefront) 16-byte loads -- no per-lane table registers;
+//        each lane reads X[k][0..P) of its node once, forms all P outputs (4 P^2 DFMA)
+//        and writes them back in place.  Warp w takes slots w, w + NWARPS, ...
+template <typename Cfg>
+struct CircTab7 {
+    double2 v[Cfg::M * Cfg::P * Cfg::P];       // [k][r][a], see rt/tables.py:circulant_spectrum
+};
+
+template <typename Cfg>
+__device__ __noinline__ void fft_f7(const double* __restrict__ U, double* __restrict__ W,
+                                    const int warp, const int lane) {
+    constexpr int NC = Cfg::NC, P = Cfg::P, H = Cfg::H, NP = NC / 8, SU = Cfg::SU, SW = Cfg::SW;
+    constexpr int NN = Cfg::NN;
+    const int n0 = (warp * NN) / Cfg::NWARPS;
+    const int nw = ((warp + 1) * NN) / Cfg::NWARPS - n0;
+    if (nw == 0) return;                                        // warp-uniform
+    const int t = lane >> 4, sq = lane & 15;
+    const bool seq_on = sq < nw * P;
+    const int dn = seq_on ? sq / P : 0, a = seq_on ? sq - dn * P : 0;
+    const int node = n0 + dn;
+    double xs[H];
+    const double* src = U + node * SU + a + t * P;
+#pragma unroll
+    for (int mm = 0; mm < H; ++mm) xs[mm] = src[2 * mm * P];
+    double2 oa[NP], ob[NP];
+    split_forward<NC>(xs, t, oa, ob);
+    if (seq_on) {
+        double2* const wa = reinterpret_cast<double2*>(W + node * SW) + a + t * P;   // slot 2p + t
+        double2* const wb = reinterpret_cast<double2*>(W + node * SW) + a - t * P;   // slot NC/2 - 2p - t
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            wa[2 * p * P] = oa[p];
+            const int sb = (p == 0 && t == 0) ? (NC / 4) : (NC / 2 - 2 * p);
+            wb[sb * P] = ob[p];
+        }
+    }
+}
+
+template <typename Cfg>
+__device__ __noinline__ void mult7(double* __restrict__ W, const double2* __restrict__ Ts, const int warp_u,
+                                   const int lane) {
+    constexpr int P = Cfg::P, NN = Cfg::NN, SW = Cfg::SW, M = Cfg::M;
+    static_assert(NN <= 32, "one lane per spatial node");
+    const bool on = lane < NN;
+    double2* const wn = reinterpret_cast<double2*>(W) + (on ? lane : 0) * (SW / 2);
+#pragma unroll 1
+    for (int k = warp_u; k < M; k += Cfg::NWARPS) {
+        double2* const w2 = wn + k * P;
+        const double2* __restrict__ tk = Ts + k * P * P;
+        double2 u[P];
+#pragma unroll
+        for (int q = 0; q < P; ++q) u[q] = w2[q];
+        if (k == 0) {                // the two real bins (X[0], X[NC/2]): no cross terms
+#pragma unroll
+            for (int r = 0; r < P; ++r) {
+                double yr = tk[r * P].x * u[0].x, yi = tk[r * P].y * u[0].y;
+#pragma unroll
+                for (int q = 1; q < P; ++q) {
+                    yr = fma(tk[r * P + q].x, u[q].x, yr);
+                    yi = fma(tk[r * P + q].y, u[q].y, yi);
+                }
+                if (on) w2[r] = make_double2(yr, yi);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < P; ++r) {
+                double y0 = tk[r * P].x * u[0].x, y1 = -(tk[r * P].y * u[0].y);
+                double y2 = tk[r * P].x * u[0].y, y3 = tk[r * P].y * u[0].x;
+#pragma unroll
+                for (int q = 1; q < P; ++q) {
+                    y0 = fma(tk[r * P + q].x, u[q].x, y0);
+                    y1 = fma(-tk[r * P + q].y, u[q].y, y1);
+                    y2 = fma(tk[r * P + q].x, u[q].y, y2);
+                    y3 = fma(tk[r * P + q].y, u[q].x, y3);
+                }
+                if (on) w2[r] = make_double2(y0 + y1, y2 + y3);
+            }
+        }
+    }
+}
+
+template <typename Cfg>
+__device__ __noinline__ void fft_i7(double* __restrict__ W, const int warp, const int lane) {
+    constexpr int NC = Cfg::NC, P = Cfg::P, H = Cfg::H, NP = NC / 8, SW = Cfg::SW;
+    constexpr int NN = Cfg::NN;
+    const int n0 = (warp * NN) / Cfg::NWARPS;
+    const int nw = ((warp + 1) * NN) / Cfg::NWARPS - n0;
+    if (nw == 0) return;                                        // warp-uniform
+    const int t = lane >> 4, sq = lane & 15;
+    const bool seq_on = sq < nw * P;
+    const int dn = seq_on ? sq / P : 0, a = seq_on ? sq - dn * P : 0;
+    const int node = n0 + dn;
+    const double2* const wa = reinterpret_cast<const double2*>(W + node * SW) + a + t * P;
+    const double2* const wb = reinterpret_cast<const double2*>(W + node * SW) + a - t * P;
+    double2 ia[NP], ib[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        ia[p] = wa[2 * p * P];
+        const int sb = (p == 0 && t == 0) ? (NC / 4) : (NC / 2 - 2 * p);
+        ib[p] = wb[sb * P];
+    }
+    __syncwarp();
+    double xs[H];
+    split_inverse<NC>(ia, ib, t, xs);
+    if (seq_on) {
+        double* dst = W + node * SW + a + t * P;
+#pragma unroll
+        for (int mm = 0; mm < H; ++mm) dst[2 * mm * P] = xs[mm];
+    }
+}
+
+template <int N, int NC, int P>
+__global__ void __launch_bounds__(Circ7Cfg<N, NC, P>::THREADS, RT7_MINB)
+k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int sg, unsigned terms,
+              int interior_only, const double* __restrict__ x, const double* __restrict__ ghost,
+              double* __restrict__ y, const __grid_constant__ CircTab7<Circ7Cfg<N, NC, P>> T) {
+    using Cfg = Circ7Cfg<N, NC, P>;
+    constexpr int NN = Cfg::NN, NT = Cfg::NT, NTP = Cfg::NTP;
+    constexpr int SU = Cfg::SU, THREADS = Cfg::THREADS;
+    extern __shared__ __align__(16) double smem7[];
+    double* const Ub = smem7;                                   // [2][U_DOUBLES]
+    double* const W = smem7 + 2 * Cfg::U_DOUBLES;               // [NN][SW]
+    double* const Ts = W + Cfg::W_DOUBLES;                      // block spectrum T[k][r][a]
+    double* const tab = Ts + Cfg::T_DOUBLES;                    // per-angle tables
+    double* const coefb = tab + Cfg::TAB_DOUBLES;               // [2][2 NN]
+    __shared__ ColMeta7 s_meta[3];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int stride = gridDim.x;
+    int it = blockIdx.x;
+    if (it >= ncols) return;
+
+    // ---- prologue: per-angle tables, block spectrum, metadata of the first two columns -- //
+    {
+        const int64_t tp0 = m.sig_th0[sg];
+        for (int e = tid; e < NT; e += THREADS) {
+            tab[e] = m.th_wt[tp0 + e];
+            tab[NT + e] = m.th_ct[tp0 + e];
+            tab[2 * NT + e] = m.th_st[tp0 + e];
+            reinterpret_cast<int*>(tab + 3 * NT)[e] = m.th_bits[tp0 + e];
+        }
+        for (int e = tid; e < Cfg::M * Cfg::P * Cfg::P; e += THREADS)
+            reinterpret_cast<double2*>(Ts)[e] = T.v[e];
+    }
+    if (warp == 0 && lane < 9) load_col_meta7(m, cols[it], s_meta[0], lane);
+    if (warp == Cfg::NWARPS - 1 && lane < 9 && it + stride < ncols)
+        load_col_meta7(m, cols[it + stride], s_meta[1], lane);
+    __syncthreads();
+
+    auto prefetch = [&](const int buf, const ColMeta7& cm) {
+        const double* __restrict__ src = x + cm.cm.slab_off;
+        double* dst = Ub + buf * Cfg::U_DOUBLES;
+        if constexpr (THREADS % NT == 0) {
+            constexpr int NODE_STEP = THREADS / NT;
+            const int n0 = tid / NT, th = tid - n0 * NT;
+            const double* __restrict__ sp = src + n0 * NTP + th;
+            double* dp = dst + n0 * SU + th;
+#pragma unroll 4
+            for (int node = n0; node < NN; node += NODE_STEP, sp += NODE_STEP * NTP, dp += NODE_STEP * SU)
+                cp_async8(dp, sp);
+        } else {
+            for (int e = tid; e < NN * NT; e += THREADS) {
+                const int node = e / NT, th = e - node * NT;
+                cp_async8(dst + node * SU + th, src + node * NTP + th);
+            }
+        }
+        const double* __restrict__ csrc = m.coef + cm.coef_off;
+        for (int e = tid; e < 2 * NN; e += THREADS) cp_async8(coefb + buf * Cfg::COEF_DOUBLES + e, csrc + e);
+        cp_async_commit();
+    };
+    prefetch(0, s_meta[0]);
+
+    const bool full = terms == RTB200_TERM_ALL;
+    const int half = tid >= Cfg::NTW ? 1 : 0;
+    const int th = tid - half * Cfg::NTW;
+    int cur = 0, ms = 0;
+    for (; it < ncols; it += stride) {
+        cp_async_wait0();
+        __syncthreads();     // U[cur] / coef[cur] landed; everybody is done with the previous column
+        const int ms1 = ms == 2 ? 0 : ms + 1, ms2 = ms1 == 2 ? 0 : ms1 + 1;
+        if (it + stride < ncols) prefetch(cur ^ 1, s_meta[ms1]);
+        if (warp == Cfg::NWARPS - 1 && lane < 9 && it + 2 * stride < ncols)
+            load_col_meta7(m, cols[it + 2 * stride], s_meta[ms2], lane);
+
+        const double* U = Ub + cur * Cfg::U_DOUBLES;
+        if (terms & RTB200_TERM_SCAT) {
+            fft_f7<Cfg>(U, W, warp, lane);
+            __syncthreads();
+            mult7<Cfg>(W, reinterpret_cast<const double2*>(Ts), __shfl_sync(0xffffffffu, warp, 0), lane);
+            __syncthreads();
+            fft_i7<Cfg>(W, warp, lane);
+            __syncthreads();
+        }
+
+        // ---- phase S: streaming terms + scattering combine -> y -------------------- //
+        {
+            const ColMeta& cm = s_meta[ms].cm;
+            const double* coef_s = coefb + cur * Cfg::COEF_DOUBLES;
+            if (th < NT && tid < 2 * Cfg::NTW) {
+                const double* ws = (terms & RTB200_TERM_SCAT) ? W + th : nullptr;
+                if (full) {
+                    if (half == 0)
+                        stream7<N, 0, true, Cfg>(cm, coef_s, tab, th, U, ws, terms, interior_only, x, ghost, y);
+                    else
+                        stream7<N, 1, true, Cfg>(cm, coef_s, tab, th, U, ws, terms, interior_only, x, ghost, y);
+                } else {
+                    if (half == 0)
+                        stream7<N, 0, false, Cfg>(cm, coef_s, tab, th, U, ws, terms, interior_only, x, ghost, y);
+                    else
+                        stream7<N, 1, false, Cfg>(cm, coef_s, tab, th, U, ws, terms, interior_only, x, ghost, y);
+                }
+            } else if (half == 0 && th < NTP) {             // pad entry of an odd row length
+                double* yc = y + cm.slab_off + th;
+                for (int n = 0; n < NN; ++n) yc[(int64_t)n * NTP] = 0.0;
+            }
+        }
+        cur ^= 1;
+        ms = ms1;
+    }
+}

@@ -154,6 +154,8 @@ extern "C" int rtb200_set_mesh(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
     {
         const char* env = getenv("RTB200_DENSE_SCATTERING");
         ctx->use_circ = !(env && env[0] == '1');
+        const char* cv = getenv("RTB200_CIRC_VERSION");
+        if (cv && cv[0] == '6') ctx->circ_version = 6;
     }
 
     // halo plan

@@ -42,7 +42,9 @@ struct Bucket {
     int32_t* grp_count_dev = nullptr;   // [n_groups] columns in the group
     // block-circulant scattering (uniform angular mesh): NC cells of P nodes; 0 = dense
     int circ_nc = 0, circ_p = 0, circ_sig = 0;
+    bool circ_conforming = false;       // no mortar face in any column of the bucket
     const double* circ_tab_dev = nullptr;
+    std::vector<double> circ_tab_host;  // same table, host copy (kernel parameter of k_apply_circ7)
 };
 
 struct NcclApi;                // resolved with dlopen in comm.cu
@@ -58,6 +60,7 @@ struct rtb200_ctx {
     int64_t n_coef = 0;
     const double* circ_pool_dev = nullptr;
     bool use_circ = true;          // RTB200_DENSE_SCATTERING=1 in the environment disables it
+    int circ_version = 7;          // RTB200_CIRC_VERSION=6 selects the one-block-per-column kernel
     int64_t launches = 0;
     int sm_count = 148;
 
