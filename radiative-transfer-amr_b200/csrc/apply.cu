@@ -341,7 +341,8 @@ static int launch_circ(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int int
     cudaError_t e;
     if constexpr (NC >= 8) {
         // persistent, prefetching kernel (apply_circ7.cuh): 2 blocks per SM walk the column list
-        if (ctx->circ_version >= 7 && b.circ_conforming) {
+        // (bulk copies need 16-byte aligned rows: slab offsets are even, so x itself must be)
+        if (ctx->circ_version >= 7 && b.circ_conforming && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
             using Cfg = Circ7Cfg<N, NC, P>;
             auto kern = k_apply_circ7<N, NC, P>;
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);

@@ -37,11 +37,33 @@ struct Circ7Cfg {
     static constexpr int THREADS = SC_WARPS * 32 > 2 * NTW ? SC_WARPS * 32 : 2 * NTW;
     static constexpr int NWARPS = THREADS / 32;
     static constexpr int NW_MAX = (NN + NWARPS - 1) / NWARPS;  // nodes per warp (even split)
-    static constexpr int SU = CircCfg<N_, NC_, P_>::SU, SW = CircCfg<N_, NC_, P_>::SW;
-    static constexpr int U_DOUBLES = (NN * SU + 1) & ~1;
+    // U row stride: even (rows are 16-byte aligned targets of the bulk copies) and with the
+    // fewest bank conflicts for the FFT gathers (a half-warp reads (node, a), node < NW_MAX,
+    // a < P at doubles node * SU + a + const)
+    static constexpr int su_conflicts(int v) {
+        int worst = 0;
+        for (int b = 0; b < 16; ++b) {
+            int c = 0;
+            for (int dn = 0; dn < NW_MAX; ++dn)
+                for (int a = 0; a < P; ++a) c += ((dn * v + a) & 15) == b;
+            worst = c > worst ? c : worst;
+        }
+        return worst;
+    }
+    static constexpr int su() {
+        int best = NTP, bc = 1 << 30;
+        for (int v = NTP; v < NTP + 32; v += 2) {
+            const int c = su_conflicts(v);
+            if (c < bc) { bc = c; best = v; }
+        }
+        return best;
+    }
+    static constexpr int SU = su(), SW = CircCfg<N_, NC_, P_>::SW;
+    static constexpr int U_DOUBLES = NN * SU;
+    static constexpr unsigned TX_BYTES = (unsigned)(sizeof(double) * (NN * NT + 2 * NN));
     static constexpr int W_DOUBLES = NN * SW;
     static constexpr int T_DOUBLES = M * P * P * 2;            // block spectrum (double2 [M][P][P])
-    static constexpr int TAB_DOUBLES = 3 * NT + (NT + 1) / 2;  // wt, wt cos, wt sin + int bits
+    static constexpr int TAB_DOUBLES = (3 * NT + (NT + 1) / 2 + 1) & ~1;  // wt, wt cos, wt sin + int bits
     static constexpr int COEF_DOUBLES = 2 * NN;
     static constexpr size_t SMEM = sizeof(double) * (size_t)(2 * U_DOUBLES + W_DOUBLES + T_DOUBLES +
                                                              TAB_DOUBLES + 2 * COEF_DOUBLES);
@@ -59,8 +81,36 @@ __device__ __forceinline__ void load_col_meta7(const DevMesh& m, const int c, Co
     if (t == 8) cm.coef_off = m.col_coef_off[c];
 }
 
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+// ---- bulk asynchronous copies (TMA, non-tensor form) completing on an mbarrier ---- //
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, const unsigned count) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(b), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, const unsigned bytes) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(b), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, const unsigned parity) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(b), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, const unsigned bytes,
+                                         unsigned long long* bar) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(s),
+        "l"(gmem), "r"(bytes), "r"(b)
+        : "memory");
+}
 
 // ---- split real FFT: forward ------------------------------------------------ //
 // xs[m] = x[2 m + t], m < NC/2.  Output: the NC/4 spectrum slots this lane owns, in
@@ -426,6 +476,7 @@ k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int 
     double* const tab = Ts + Cfg::T_DOUBLES;                    // per-angle tables
     double* const coefb = tab + Cfg::TAB_DOUBLES;               // [2][2 NN]
     __shared__ ColMeta7 s_meta[3];
+    __shared__ __align__(8) unsigned long long s_bar[2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int stride = gridDim.x;
     int it = blockIdx.x;
@@ -443,31 +494,32 @@ k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int 
         for (int e = tid; e < Cfg::M * Cfg::P * Cfg::P; e += THREADS)
             reinterpret_cast<double2*>(Ts)[e] = T.v[e];
     }
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
     if (warp == 0 && lane < 9) load_col_meta7(m, cols[it], s_meta[0], lane);
     if (warp == Cfg::NWARPS - 1 && lane < 9 && it + stride < ncols)
         load_col_meta7(m, cols[it + stride], s_meta[1], lane);
     __syncthreads();
 
+    // One lane issues the bulk copies of a column (NN rows of the slab + the coefficient
+    // samples); they complete on the buffer's mbarrier.
     auto prefetch = [&](const int buf, const ColMeta7& cm) {
-        const double* __restrict__ src = x + cm.cm.slab_off;
-        double* dst = Ub + buf * Cfg::U_DOUBLES;
-        if constexpr (THREADS % NT == 0) {
-            constexpr int NODE_STEP = THREADS / NT;
-            const int n0 = tid / NT, th = tid - n0 * NT;
-            const double* __restrict__ sp = src + n0 * NTP + th;
-            double* dp = dst + n0 * SU + th;
-#pragma unroll 4
-            for (int node = n0; node < NN; node += NODE_STEP, sp += NODE_STEP * NTP, dp += NODE_STEP * SU)
-                cp_async8(dp, sp);
-        } else {
-            for (int e = tid; e < NN * NT; e += THREADS) {
-                const int node = e / NT, th = e - node * NT;
-                cp_async8(dst + node * SU + th, src + node * NTP + th);
-            }
+        if (warp == Cfg::NWARPS - 1 && lane == 16) {
+            // order the block's earlier generic-proxy reads of the buffer before the
+            // async-proxy writes (the block barrier made them visible to this thread)
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            mbar_expect_tx(&s_bar[buf], Cfg::TX_BYTES);
+            const double* __restrict__ src = x + cm.cm.slab_off;
+            double* dst = Ub + buf * Cfg::U_DOUBLES;
+#pragma unroll 1
+            for (int node = 0; node < NN; ++node)
+                bulk_g2s(dst + node * SU, src + node * NTP, (unsigned)(sizeof(double) * NT), &s_bar[buf]);
+            bulk_g2s(coefb + buf * Cfg::COEF_DOUBLES, m.coef + cm.coef_off,
+                     (unsigned)(sizeof(double) * 2 * NN), &s_bar[buf]);
         }
-        const double* __restrict__ csrc = m.coef + cm.coef_off;
-        for (int e = tid; e < 2 * NN; e += THREADS) cp_async8(coefb + buf * Cfg::COEF_DOUBLES + e, csrc + e);
-        cp_async_commit();
     };
     prefetch(0, s_meta[0]);
 
@@ -475,14 +527,16 @@ k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int 
     const int half = tid >= Cfg::NTW ? 1 : 0;
     const int th = tid - half * Cfg::NTW;
     int cur = 0, ms = 0;
+    unsigned phase = 0;      // bit b: parity of the next completion of buffer b
     for (; it < ncols; it += stride) {
-        cp_async_wait0();
-        __syncthreads();     // U[cur] / coef[cur] landed; everybody is done with the previous column
+        __syncthreads();     // everybody is done with the previous column (U[cur ^ 1], W are free)
         const int ms1 = ms == 2 ? 0 : ms + 1, ms2 = ms1 == 2 ? 0 : ms1 + 1;
         if (it + stride < ncols) prefetch(cur ^ 1, s_meta[ms1]);
         if (warp == Cfg::NWARPS - 1 && lane < 9 && it + 2 * stride < ncols)
             load_col_meta7(m, cols[it + 2 * stride], s_meta[ms2], lane);
 
+        mbar_wait(&s_bar[cur], (phase >> cur) & 1u);     // U[cur] / coef[cur] landed
+        phase ^= 1u << cur;
         const double* U = Ub + cur * Cfg::U_DOUBLES;
         if (terms & RTB200_TERM_SCAT) {
             fft_f7<Cfg>(U, W, warp, lane);
