@@ -80,7 +80,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -262,12 +262,20 @@ def run_b200(args):
         return float(ms.item())
 
     step = lambda: op.apply_slab(x, y, 15, True)          # noqa: E731
-    for _ in range(args.warmup):
-        step()
-    l0 = op.launch_count()
+    # the clock sampler (nvidia-smi, 20 ms period) runs over the warm-up steps and the timed
+    # region: the timed region alone can be shorter than one sampling period
     with ClockSampler(local) as clk:
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize(dev)
+        l0 = op.launch_count()
         ms_total = timed(step, args.steps)
-    launches = op.launch_count() - l0
+        launches = op.launch_count() - l0
+        if len(clk.rows) < 5:                             # keep the GPU under the same load a little longer
+            t_end = time.perf_counter() + 0.3
+            while time.perf_counter() < t_end:
+                step()
+            torch.cuda.synchronize(dev)
     ms_step = ms_total / args.steps
     gdofs = n_total / ms_step / 1e6
     clocks = clk.summary()
@@ -283,7 +291,7 @@ def run_b200(args):
     nt = int(flat.sig_nt.max())
     scat_flops = 2.0 * nt * n_total
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "kernel": "k_apply",
+                "frac": achieved / hbm_peak, "traffic": None, "kernel": op.apply_kernel_name(),
                 "peak_source": peak_src, "algorithmic_bytes_per_dof": BYTES_PER_DOF,
                 "note": "dense angular scattering costs 2*Ntheta = %d flop/DoF, FP64-bound on "
                         "B200; see fp64 and no_scattering" % (2 * nt),

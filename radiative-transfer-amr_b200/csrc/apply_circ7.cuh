@@ -22,6 +22,7 @@
 // Shared memory per block at (N, NC, P) = (5, 32, 5): 2 x 33.0 KB (U) + 34.0 KB (W)
 // + 6.4 KB (block spectrum) + 4.5 KB (angle tables) + 0.8 KB = 111.7 KB -> 2 blocks / SM.
 #pragma once
+#include <utility>
 #ifndef RT7_MINB
 #define RT7_MINB 2
 #endif
@@ -36,7 +37,11 @@ struct Circ7Cfg {
     static constexpr int NTW = (NT + 31) / 32 * 32;            // S role: threads per half
     static constexpr int THREADS = SC_WARPS * 32 > 2 * NTW ? SC_WARPS * 32 : 2 * NTW;
     static constexpr int NWARPS = THREADS / 32;
-    static constexpr int NW_MAX = (NN + NWARPS - 1) / NWARPS;  // nodes per warp (even split)
+    // The last warp is the producer (bulk copies of the next column, metadata two columns
+    // ahead: long-latency global loads); when the block has a warp to spare it is kept out
+    // of the FFT and block-product phases so that nobody waits for it at their barriers.
+    static constexpr int WORK_WARPS = SC_WARPS < NWARPS ? NWARPS - 1 : NWARPS;
+    static constexpr int NW_MAX = (NN + WORK_WARPS - 1) / WORK_WARPS;  // nodes per warp (even split)
     // U row stride: even (rows are 16-byte aligned targets of the bulk copies) and with the
     // fewest bank conflicts for the FFT gathers (a half-warp reads (node, a), node < NW_MAX,
     // a < P at doubles node * SU + a + const)
@@ -349,8 +354,9 @@ __device__ __noinline__ void stream7(
 //        F: U -> spectrum slots in W;  I: slots -> real row W[node][theta], in place
 //        (only the owning warp touches a node's row: __syncwarp is enough).
 // M:     lane = spatial node, the frequency slot k is warp-uniform: the P x P complex
-//        block T[k] is read from shared memory with warp-uniform (broadcast, one
-//        wavefront) 16-byte loads -- no per-lane table registers;
+//        block T[k] is read from shared memory with warp-uniform (broadcast) 16-byte
+//        loads -- no per-lane table registers (a constant-bank table was measured slower:
+//        the uniform loads miss in the constant cache);
 //        each lane reads X[k][0..P) of its node once, forms all P outputs (4 P^2 DFMA)
 //        and writes them back in place.  Warp w takes slots w, w + NWARPS, ...
 template <typename Cfg>
@@ -363,9 +369,10 @@ __device__ __noinline__ void fft_f7(const double* __restrict__ U, double* __rest
                                     const int warp, const int lane) {
     constexpr int NC = Cfg::NC, P = Cfg::P, H = Cfg::H, NP = NC / 8, SU = Cfg::SU, SW = Cfg::SW;
     constexpr int NN = Cfg::NN;
-    const int n0 = (warp * NN) / Cfg::NWARPS;
-    const int nw = ((warp + 1) * NN) / Cfg::NWARPS - n0;
-    if (nw == 0) return;                                        // warp-uniform
+    if (warp >= Cfg::WORK_WARPS) return;                        // warp-uniform
+    const int n0 = (warp * NN) / Cfg::WORK_WARPS;
+    const int nw = ((warp + 1) * NN) / Cfg::WORK_WARPS - n0;
+    if (nw == 0) return;
     const int t = lane >> 4, sq = lane & 15;
     const bool seq_on = sq < nw * P;
     const int dn = seq_on ? sq / P : 0, a = seq_on ? sq - dn * P : 0;
@@ -388,56 +395,101 @@ __device__ __noinline__ void fft_f7(const double* __restrict__ U, double* __rest
     }
 }
 
+// one complex slot: y[r] = sum_q T[k][r][q] u[q], in place
+template <typename Cfg>
+__device__ __forceinline__ void mult7_one(double2* const w2, const double2* __restrict__ tk, const bool on) {
+    constexpr int P = Cfg::P;
+    double2 u[P];
+#pragma unroll
+    for (int q = 0; q < P; ++q) u[q] = w2[q];
+#pragma unroll
+    for (int r = 0; r < P; ++r) {
+        double y0 = tk[r * P].x * u[0].x, y1 = -(tk[r * P].y * u[0].y);
+        double y2 = tk[r * P].x * u[0].y, y3 = tk[r * P].y * u[0].x;
+#pragma unroll
+        for (int q = 1; q < P; ++q) {
+            y0 = fma(tk[r * P + q].x, u[q].x, y0);
+            y1 = fma(-tk[r * P + q].y, u[q].y, y1);
+            y2 = fma(tk[r * P + q].x, u[q].y, y2);
+            y3 = fma(tk[r * P + q].y, u[q].x, y3);
+        }
+        if (on) w2[r] = make_double2(y0 + y1, y2 + y3);
+    }
+}
+
 template <typename Cfg>
 __device__ __noinline__ void mult7(double* __restrict__ W, const double2* __restrict__ Ts, const int warp_u,
                                    const int lane) {
-    constexpr int P = Cfg::P, NN = Cfg::NN, SW = Cfg::SW, M = Cfg::M;
+    constexpr int P = Cfg::P, NN = Cfg::NN, SW = Cfg::SW, M = Cfg::M, WW = Cfg::WORK_WARPS;
     static_assert(NN <= 32, "one lane per spatial node");
+    if (warp_u >= WW) return;
     const bool on = lane < NN;
     double2* const wn = reinterpret_cast<double2*>(W) + (on ? lane : 0) * (SW / 2);
-#pragma unroll 1
-    for (int k = warp_u; k < M; k += Cfg::NWARPS) {
-        double2* const w2 = wn + k * P;
-        const double2* __restrict__ tk = Ts + k * P * P;
+    int k = warp_u;
+    if (k == 0) {                    // the two real bins (X[0], X[NC/2]): no cross terms
+        double2* const w2 = wn;
         double2 u[P];
 #pragma unroll
         for (int q = 0; q < P; ++q) u[q] = w2[q];
-        if (k == 0) {                // the two real bins (X[0], X[NC/2]): no cross terms
 #pragma unroll
-            for (int r = 0; r < P; ++r) {
-                double yr = tk[r * P].x * u[0].x, yi = tk[r * P].y * u[0].y;
+        for (int r = 0; r < P; ++r) {
+            double yr = Ts[r * P].x * u[0].x, yi = Ts[r * P].y * u[0].y;
 #pragma unroll
-                for (int q = 1; q < P; ++q) {
-                    yr = fma(tk[r * P + q].x, u[q].x, yr);
-                    yi = fma(tk[r * P + q].y, u[q].y, yi);
-                }
-                if (on) w2[r] = make_double2(yr, yi);
+            for (int q = 1; q < P; ++q) {
+                yr = fma(Ts[r * P + q].x, u[q].x, yr);
+                yi = fma(Ts[r * P + q].y, u[q].y, yi);
             }
-        } else {
+            if (on) w2[r] = make_double2(yr, yi);
+        }
+        k += WW;
+    }
+    // pairs of slots (k, k + WW) interleaved: 8 independent chains per output row
+#pragma unroll 1
+    for (; k + WW < M; k += 2 * WW) {
+        double2* const wa = wn + k * P;
+        double2* const wb = wn + (k + WW) * P;
+        const double2* __restrict__ ta = Ts + k * P * P;
+        const double2* __restrict__ tb = Ts + (k + WW) * P * P;
+        double2 ua[P], ub[P];
 #pragma unroll
-            for (int r = 0; r < P; ++r) {
-                double y0 = tk[r * P].x * u[0].x, y1 = -(tk[r * P].y * u[0].y);
-                double y2 = tk[r * P].x * u[0].y, y3 = tk[r * P].y * u[0].x;
+        for (int q = 0; q < P; ++q) {
+            ua[q] = wa[q];
+            ub[q] = wb[q];
+        }
 #pragma unroll
-                for (int q = 1; q < P; ++q) {
-                    y0 = fma(tk[r * P + q].x, u[q].x, y0);
-                    y1 = fma(-tk[r * P + q].y, u[q].y, y1);
-                    y2 = fma(tk[r * P + q].x, u[q].y, y2);
-                    y3 = fma(tk[r * P + q].y, u[q].x, y3);
-                }
-                if (on) w2[r] = make_double2(y0 + y1, y2 + y3);
+        for (int r = 0; r < P; ++r) {
+            double a0 = ta[r * P].x * ua[0].x, a1 = -(ta[r * P].y * ua[0].y);
+            double a2 = ta[r * P].x * ua[0].y, a3 = ta[r * P].y * ua[0].x;
+            double b0 = tb[r * P].x * ub[0].x, b1 = -(tb[r * P].y * ub[0].y);
+            double b2 = tb[r * P].x * ub[0].y, b3 = tb[r * P].y * ub[0].x;
+#pragma unroll
+            for (int q = 1; q < P; ++q) {
+                a0 = fma(ta[r * P + q].x, ua[q].x, a0);
+                a1 = fma(-ta[r * P + q].y, ua[q].y, a1);
+                a2 = fma(ta[r * P + q].x, ua[q].y, a2);
+                a3 = fma(ta[r * P + q].y, ua[q].x, a3);
+                b0 = fma(tb[r * P + q].x, ub[q].x, b0);
+                b1 = fma(-tb[r * P + q].y, ub[q].y, b1);
+                b2 = fma(tb[r * P + q].x, ub[q].y, b2);
+                b3 = fma(tb[r * P + q].y, ub[q].x, b3);
+            }
+            if (on) {
+                wa[r] = make_double2(a0 + a1, a2 + a3);
+                wb[r] = make_double2(b0 + b1, b2 + b3);
             }
         }
     }
+    if (k < M) mult7_one<Cfg>(wn + k * P, Ts + k * P * P, on);
 }
 
 template <typename Cfg>
 __device__ __noinline__ void fft_i7(double* __restrict__ W, const int warp, const int lane) {
     constexpr int NC = Cfg::NC, P = Cfg::P, H = Cfg::H, NP = NC / 8, SW = Cfg::SW;
     constexpr int NN = Cfg::NN;
-    const int n0 = (warp * NN) / Cfg::NWARPS;
-    const int nw = ((warp + 1) * NN) / Cfg::NWARPS - n0;
-    if (nw == 0) return;                                        // warp-uniform
+    if (warp >= Cfg::WORK_WARPS) return;                        // warp-uniform
+    const int n0 = (warp * NN) / Cfg::WORK_WARPS;
+    const int nw = ((warp + 1) * NN) / Cfg::WORK_WARPS - n0;
+    if (nw == 0) return;
     const int t = lane >> 4, sq = lane & 15;
     const bool seq_on = sq < nw * P;
     const int dn = seq_on ? sq / P : 0, a = seq_on ? sq - dn * P : 0;

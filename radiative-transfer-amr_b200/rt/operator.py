@@ -293,6 +293,16 @@ class RTOperator:
     def launch_count(self) -> int:
         return int(self.lib.rtb200_launch_count(self.ctx))
 
+    def apply_kernel_name(self) -> str:
+        """Name of the kernel that carries (most of) an apply on this mesh: the
+        block-circulant FFT kernel when every column has a uniform angular mesh the
+        library is compiled for, else the dense (DMMA) kernel."""
+        import os
+        dense = os.environ.get("RTB200_DENSE_SCATTERING") == "1"
+        if not dense and len(self.circ[2]) and (np.asarray(self.circ[2]) >= 0).all():
+            return "k_apply_circ" if os.environ.get("RTB200_CIRC_VERSION") == "6" else "k_apply_circ7"
+        return "k_apply"
+
     # ------------------------------------------------------------------ #
     def gmres(self, b_slab, x_slab, restart: int = 50, max_it: int = 5000, rtol: float = 1e-15,
               atol: float = 1e-15, divtol: float = None, orth: int = 0, pc: int = 0,
