@@ -1,0 +1,75 @@
+"""Worker of tests/test_gpu_multi.py: one process per GPU (torchrun), NCCL.
+
+Every rank builds its part of the FlatMesh with the reference's column partition
+(np.array_split of the sorted column keys, mass_matrix.py:50-51), applies the
+operator to its slice of the golden input vector (face traces of neighbour ranks
+arrive through the library's NCCL halo exchange) and solves the golden system with
+the distributed GMRES.  Rank 0 gathers the pieces and writes them for the test.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _log(msg):
+    if os.environ.get("RTB200_TEST_VERBOSE"):
+        print("[rank %s] %s" % (os.environ.get("RANK"), msg), file=sys.stderr, flush=True)
+
+
+def main():
+    case, out = sys.argv[1], sys.argv[2]
+    import torch
+    import torch.distributed as dist
+    from conftest import load_golden
+    from rt_b200.rt import RTOperator
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    mesh, d, prob = load_golden(case)
+    op = RTOperator(mesh, prob.kappa, prob.sigma, prob.Phi, device=dev, rank=rank, nranks=world)
+    _log("operator built")
+    op.comm_init(rank, world)
+    _log("communicator up")
+    f = op.flat
+    sl = slice(f.dof0, f.dof0 + f.n_dof)
+    y_loc = op.mult(d["x"][sl].copy())
+    yi_loc = op.mult((d["x"] * d["mask"])[sl].copy(), interior_only=True)
+    _log("applies done")
+    # distributed GMRES on the golden right-hand side (dof order, boundary rows zero)
+    mask = d["mask"].astype(bool)
+    rhs_full = np.zeros(mask.size)
+    rhs_full[mask] = d["rhs"]
+    b = op.to_slab(rhs_full[sl].copy())
+    x0 = op.to_slab((d["f_vec"] * mask)[sl].copy())
+    info = op.gmres(b, x0, restart=50, max_it=3000, rtol=1e-13, atol=0.0, x0_nonzero=True)
+    u_loc = op.from_slab(x0).cpu().numpy()
+    _log("gmres done: %s" % info)
+    parts = [None] * world
+    dist.all_gather_object(parts, (int(f.dof0), y_loc, yi_loc, u_loc, int(f.n_ghost)))
+    if rank == 0:
+        parts.sort(key=lambda p: p[0])
+        np.savez(out, y=np.concatenate([p[1] for p in parts]),
+                 yi=np.concatenate([p[2] for p in parts]),
+                 u=np.concatenate([p[3] for p in parts]),
+                 ghosts=np.array([p[4] for p in parts]),
+                 iterations=info["iterations"], reason=info["reason"])
+    dist.barrier()
+    op.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    try:
+        main()
+    except BaseException:            # never leave the other ranks waiting in a collective
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
