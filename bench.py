@@ -73,14 +73,16 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index: int, enabled: bool = True):
+        self.index, self.rows, self.proc, self.enabled = index, [], None, enabled
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "20"],
+                 "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -262,20 +264,22 @@ def run_b200(args):
         return float(ms.item())
 
     step = lambda: op.apply_slab(x, y, 15, True)          # noqa: E731
-    # the clock sampler (nvidia-smi, 20 ms period) runs over the warm-up steps and the timed
-    # region: the timed region alone can be shorter than one sampling period
-    with ClockSampler(local) as clk:
+    # the clock sampler (nvidia-smi, 100 ms period, rank 0 only: several pollers at a short
+    # period were measured to slow the kernels down) runs over the warm-up steps, the timed
+    # region and a short tail under the same load: the timed region alone can be shorter
+    # than one sampling period
+    with ClockSampler(local, enabled=(rank == 0)) as clk:
         for _ in range(args.warmup):
             step()
         torch.cuda.synchronize(dev)
         l0 = op.launch_count()
         ms_total = timed(step, args.steps)
         launches = op.launch_count() - l0
-        if len(clk.rows) < 5:                             # keep the GPU under the same load a little longer
-            t_end = time.perf_counter() + 0.3
-            while time.perf_counter() < t_end:
-                step()
-            torch.cuda.synchronize(dev)
+        # keep the GPUs under the same load for ~0.5 s more so that the sampler sees it
+        # (same count on every rank: ms_total is the max over ranks)
+        for _ in range(int(min(2000, 500.0 / max(ms_total / args.steps, 1e-3)))):
+            step()
+        torch.cuda.synchronize(dev)
     ms_step = ms_total / args.steps
     gdofs = n_total / ms_step / 1e6
     clocks = clk.summary()
