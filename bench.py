@@ -130,71 +130,89 @@ def _cpu_part(i):
     return i
 
 
+class CpuArm:
+    """The reference's way of applying the operator on the host: an explicitly assembled
+    sparse matrix (assembled once by the oracle restatement of src/rt for a bounded sample
+    of the workload) multiplied with scipy CSR SpMV on `nproc` host cores (one forked
+    process per row block with equal numbers of non-zeros; scipy's SpMV is single-threaded
+    and holds the GIL)."""
+
+    def __init__(self, nproc: int, sample):
+        import multiprocessing as mp
+        import rt_b200  # noqa: F401
+        from rt_b200 import configs
+        from oracle import rt_oracle as O
+        ns, na, nd = sample
+        prob = configs.two_strong_scatterers(LS)
+        mesh = configs.build_mesh(LS, [False, False], nd, nref_ang=na, nref_spt=ns)
+        t0 = time.perf_counter()
+        sysm = O.assemble(mesh, prob.kappa, prob.sigma, prob.Phi)
+        A_ii, _ = O.restrict(sysm["A"], sysm["mask"])
+        self.t_assemble = time.perf_counter() - t0
+        self.A_ii, self.n, self.nproc = A_ii, A_ii.shape[0], nproc
+        ctx = mp.get_context("fork")
+        _CPU["x"] = ctx.RawArray("d", self.n)
+        _CPU["y"] = ctx.RawArray("d", self.n)
+        self.x = np.frombuffer(_CPU["x"], dtype=np.float64)
+        self.x[:] = np.random.default_rng(1).standard_normal(self.n)
+        self.y = np.frombuffer(_CPU["y"], dtype=np.float64)
+        cum = A_ii.indptr
+        bounds = np.searchsorted(cum, np.linspace(0, cum[-1], nproc + 1)).astype(int)
+        bounds[0], bounds[-1] = 0, self.n
+        _CPU["bounds"] = bounds
+        _CPU["blocks"] = [A_ii[bounds[i]:bounds[i + 1]] for i in range(nproc)]
+        self.pool = ctx.Pool(nproc) if nproc > 1 else None
+        self.sample = ("uniform %dx%d columns x %d cells, ndofs %s (%d interior DoF, nnz %d); "
+                       "oracle-assembled A_ii, scipy CSR SpMV in %d row-block process(es)"
+                       % (2 ** ns, 2 ** ns, 2 ** na, nd, self.n, A_ii.nnz, nproc))
+
+    def step(self) -> float:
+        """One y = A_ii x; returns the wall time in seconds."""
+        t = time.perf_counter()
+        if self.pool is None:
+            _cpu_part(0)
+        else:
+            self.pool.map(_cpu_part, range(self.nproc), chunksize=1)
+        return time.perf_counter() - t
+
+    def check(self) -> bool:
+        return bool(np.allclose(self.y, self.A_ii @ self.x))
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+        _CPU.clear()
+
+
 def cpu_reference_arm(nproc: int, sample=(3, 5, [5, 5, 5]), reps: int = 5):
-    """Assemble A_ii for a bounded sample of the workload with the oracle and time
-    CSR SpMV on `nproc` host cores (one forked process per row block; scipy's
-    SpMV is single-threaded and holds the GIL)."""
-    import multiprocessing as mp
-    import rt_b200  # noqa: F401
-    from rt_b200 import configs
-    from oracle import rt_oracle as O
-    ns, na, nd = sample
-    prob = configs.two_strong_scatterers(LS)
-    mesh = configs.build_mesh(LS, [False, False], nd, nref_ang=na, nref_spt=ns)
-    t0 = time.perf_counter()
-    sysm = O.assemble(mesh, prob.kappa, prob.sigma, prob.Phi)
-    A_ii, _ = O.restrict(sysm["A"], sysm["mask"])
-    t_asm = time.perf_counter() - t0
-    n = A_ii.shape[0]
-    ctx = mp.get_context("fork")
-    _CPU["x"] = ctx.RawArray("d", n)
-    _CPU["y"] = ctx.RawArray("d", n)
-    x = np.frombuffer(_CPU["x"], dtype=np.float64)
-    x[:] = np.random.default_rng(1).standard_normal(n)
-    y = np.frombuffer(_CPU["y"], dtype=np.float64)
-    # row blocks with equal numbers of non-zeros
-    cum = A_ii.indptr
-    bounds = np.searchsorted(cum, np.linspace(0, cum[-1], nproc + 1)).astype(int)
-    bounds[0], bounds[-1] = 0, n
-    _CPU["bounds"] = bounds
-    _CPU["blocks"] = [A_ii[bounds[i]:bounds[i + 1]] for i in range(nproc)]
-    ts = []
-    if nproc == 1:
-        _cpu_part(0)
-        for _ in range(reps):
-            t = time.perf_counter(); _cpu_part(0); ts.append(time.perf_counter() - t)
-    else:
-        with ctx.Pool(nproc) as pool:
-            pool.map(_cpu_part, range(nproc), chunksize=1)
-            for _ in range(reps):
-                t = time.perf_counter()
-                pool.map(_cpu_part, range(nproc), chunksize=1)
-                ts.append(time.perf_counter() - t)
-    ok = bool(np.allclose(y, A_ii @ x))
-    _CPU.clear()
+    """Best / median of `reps` SpMV steps on a bounded sample (bench cpu_baseline leg)."""
+    arm = CpuArm(nproc, sample)
+    arm.step()
+    ts = [arm.step() for _ in range(reps)]
+    ok = arm.check()
+    out = {"n": int(arm.n), "nnz": int(arm.A_ii.nnz), "t_apply_s": float(min(ts)),
+           "t_apply_med_s": float(np.median(ts)), "t_assemble_s": float(arm.t_assemble),
+           "sample": arm.sample}
+    arm.close()
     assert ok
-    return {"n": int(n), "nnz": int(A_ii.nnz), "t_apply_s": float(min(ts)),
-            "t_apply_med_s": float(np.median(ts)), "t_assemble_s": float(t_asm),
-            "sample": "uniform %dx%d columns x %d cells, ndofs %s (%d interior DoF, nnz %d); "
-                      "oracle-assembled A_ii, scipy CSR SpMV in %d row-block process(es)"
-                      % (2 ** ns, 2 ** ns, 2 ** na, nd, n, A_ii.nnz, nproc)}
+    return out
 
 
 def run_reference(args):
+    """`--impl reference`: W warm-up + K timed steps, each step one SpMV of the bounded
+    sample with every host core; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     ns, na, nd = WORKLOADS[args.workload]
-    sample = (min(ns, 3), na, nd)
-    # warm-up + steps: each step = best-of-reps SpMV of the bounded sample
-    res = None
-    ts = []
-    for it in range(args.warmup + args.steps):
-        res = cpu_reference_arm(cores, sample, reps=3) if res is None else res
-        if it >= args.warmup:
-            ts.append(res["t_apply_med_s"])
-    gdofs = res["n"] / np.mean(ts) / 1e9
+    arm = CpuArm(cores, (min(ns, 4), na, nd))
+    for _ in range(max(args.warmup, 1)):
+        arm.step()
+    ts = [arm.step() for _ in range(args.steps)]
+    assert arm.check()
+    gdofs = arm.n / np.mean(ts) / 1e9
     line = {"impl": "reference", "metric": "transport_operator_apply_throughput",
             "value": gdofs, "unit": "GDoF/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": float(np.mean(ts) * 1e3),
@@ -203,9 +221,10 @@ def run_reference(args):
             "config": {"workload": args.workload, "note": "CPU arm runs a bounded sample of the "
                        "workload; throughput per DoF is size-independent for CSR SpMV"},
             "cpu_baseline": {"value": gdofs, "unit": "GDoF/s", "cores": cores, "kind": "port",
-                             "sample": res["sample"], "assemble_s": res["t_assemble_s"]},
+                             "sample": arm.sample, "assemble_s": arm.t_assemble},
             "e2e": {"value": gdofs, "unit": "GDoF/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
+    arm.close()
     print(json.dumps(line))
 
 
@@ -297,11 +316,15 @@ def run_b200(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": None, "kernel": op.apply_kernel_name(),
                 "peak_source": peak_src, "algorithmic_bytes_per_dof": BYTES_PER_DOF,
-                "note": "dense angular scattering costs 2*Ntheta = %d flop/DoF, FP64-bound on "
-                        "B200; see fp64 and no_scattering" % (2 * nt),
-                "fp64": {"achieved_tflops": scat_flops / world / (ms_step * 1e-3) / 1e12,
-                         "peak_tflops": FP64_PEAK_TFLOPS,
-                         "frac": scat_flops / world / (ms_step * 1e-3) / 1e12 / FP64_PEAK_TFLOPS},
+                "note": "a dense angular scattering product would cost 2*Ntheta = %d flop/DoF "
+                        "(FP64-bound at 28%% of the HBM roofline); uniform angular meshes use the "
+                        "block-circulant FFT form instead" % (2 * nt),
+                "fp64_dense_equivalent": {
+                    "tflops": scat_flops / world / (ms_step * 1e-3) / 1e12,
+                    "peak_tflops": FP64_PEAK_TFLOPS,
+                    "note": "2*Ntheta flop/DoF a dense product would need per apply, over the "
+                            "apply time; above the FP64 peak when the FFT path is used "
+                            "(it needs ~45 FP64 instructions/DoF instead of 320 flop)"},
                 "no_scattering": {"ms_per_step": ms_ns,
                                   "achieved": BYTES_PER_DOF * (n_total / world) / (ms_ns * 1e-3) / 1e9,
                                   "frac": BYTES_PER_DOF * (n_total / world) / (ms_ns * 1e-3) / 1e9 / hbm_peak}}
@@ -373,7 +396,7 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        r = cpu_reference_arm(1, (min(ns, 3), na, nd), reps=5)
+        r = cpu_reference_arm(1, (min(ns, 4), na, nd), reps=5)
         cpu = {"value": r["n"] / r["t_apply_s"] / 1e9, "unit": "GDoF/s", "cores": 1,
                "kind": "port", "sample": r["sample"], "assemble_s": r["t_assemble_s"],
                "host_cores_available": cores}
