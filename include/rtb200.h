@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define RTB200_ABI_VERSION 2
+#define RTB200_ABI_VERSION 3
 
 /* error codes */
 #define RTB200_OK            0
@@ -235,6 +235,17 @@ int64_t rtb200_gmres_work_bytes(const rtb200_ctx* ctx, int restart);
 int  rtb200_gmres(rtb200_ctx* ctx, const double* b_dev, double* x_dev,
                   const rtb200_gmres_params* prm, rtb200_gmres_result* res,
                   double* hist_host, void* work_dev, int64_t work_bytes, void* stream);
+
+/* ---- preconditioner: z = mask . (M - S)^{-1} r, the inverse of the reference's
+ *      "preconditioner matrix" (preconditioner_matrix.py:22-267, block diagonal
+ *      over (column, spatial node)) through the block-circulant structure of the
+ *      scattering kernel; uniform angular meshes (>= 8 cells) only, otherwise
+ *      RTB200_EUNSUPPORTED.  rtb200_gmres applies it from the left when
+ *      params.pc = 1.  x and y must not alias. --------------------------- */
+int  rtb200_pc_apply(rtb200_ctx* ctx, const double* x_slab_dev, double* y_slab_dev, void* stream);
+/* extinction floor kappa_eff = kappa + shift / min(dx, dy) used inside the preconditioner
+ * (vacuum regions make M - S singular); default 1, 0 = exact (M - S)^{-1} */
+int  rtb200_pc_set_shift(rtb200_ctx* ctx, double shift);
 
 /* ---- multi-GPU: one process per GPU; columns split like the reference's
  *      np.array_split(sorted keys, size)[rank] (mass_matrix.py:50-51).

@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_NXY = 12
 MAX_NTH = 16
 
@@ -87,6 +87,8 @@ SYMBOLS = {
     "rtb200_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "rtb200_comm_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
     "rtb200_halo_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rtb200_pc_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rtb200_pc_set_shift": (C.c_int, [C.c_void_p, C.c_double]),
     "rtb200_launch_count": (C.c_int64, [C.c_void_p]),
 }
 

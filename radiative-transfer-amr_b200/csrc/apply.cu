@@ -569,3 +569,6 @@ extern "C" int rtb200_mask(rtb200_ctx* ctx, double* x_slab_dev, int keep, void* 
     RT_CUDA(ctx, cudaGetLastError());
     return RTB200_OK;
 }
+
+// node-wise block-Jacobi preconditioner (shares the transforms of k_apply_circ7)
+#include "precond_circ.cuh"

@@ -1,0 +1,251 @@
+// Node-wise block-Jacobi preconditioner  z = mask . (M - S)^{-1} r  for columns with
+// a uniform angular mesh (block-circulant scattering, NC >= 8).
+//
+// M - S (the reference's "preconditioner matrix", preconditioner_matrix.py:116-267) is
+// block diagonal over (column, spatial node); the block of a node is
+//     B = mk diag(wt) - ms G                       (NT x NT, NT = NC P angular DoFs)
+// with G block circulant in the cell index.  The FFT over the cell index that the
+// apply kernel uses for G x block-diagonalises B as well: per frequency k a P x P
+// complex system
+//     (mk diag(wt_a) - ms Chat[k]) Z[k] = X[k],
+// solved here by Gaussian elimination without pivoting (B is symmetric positive
+// definite for sigma <= kappa, and so is every frequency block).  Chat[k] is recovered
+// from the apply kernel's table T (rt/tables.py:circulant_spectrum):
+//     Chat[0] = nc T[0].re, Chat[nc/2] = nc T[0].im, Chat[k] = 2 nc T[k].
+// With the transform conventions of fft_real.cuh (forward slot k = 2 X[k] for k > 0,
+// inverse returns nc x):  z = inverse( slot0: Z, slot k: Z[k] from rhs slot / 2 ) / nc.
+//
+// Vacuum regions (kappa = 0: M - S vanishes there, pure advection) would make the blocks
+// singular, so the extinction is floored: kappa_eff = kappa + shift / min(dx, dy) -- the
+// magnitude of the advection operator on the column -- with ctx->pc_shift = 1 by default
+// (rtb200_pc_set_shift; 0 gives the exact (M - S)^{-1}).  Any SPD choice is a valid
+// preconditioner; it only changes the iteration count.
+//
+// Rows of inflow-boundary DoFs are zero in r (GMRES vectors) and are zeroed again in z
+// (k_mask): on boundary nodes the result is the interior part of the unrestricted
+// inverse, a fixed linear approximation of (M - S)_ii^{-1} -- still a valid
+// preconditioner.  One block per column; transforms shared with k_apply_circ7.
+#pragma once
+
+template <int P>
+__device__ __forceinline__ void solve_complex(double (&ar)[P][P], double (&ai)[P][P], double (&br)[P],
+                                              double (&bi)[P]) {
+    double pr[P], pi[P];
+#pragma unroll
+    for (int c = 0; c < P; ++c) {
+        const double d = 1.0 / fma(ar[c][c], ar[c][c], ai[c][c] * ai[c][c]);
+        pr[c] = ar[c][c] * d;
+        pi[c] = -(ai[c][c] * d);
+#pragma unroll
+        for (int r = c + 1; r < P; ++r) {
+            const double lr = ar[r][c] * pr[c] - ai[r][c] * pi[c];
+            const double li = ar[r][c] * pi[c] + ai[r][c] * pr[c];
+#pragma unroll
+            for (int q = c + 1; q < P; ++q) {
+                ar[r][q] -= lr * ar[c][q] - li * ai[c][q];
+                ai[r][q] -= lr * ai[c][q] + li * ar[c][q];
+            }
+            br[r] -= lr * br[c] - li * bi[c];
+            bi[r] -= lr * bi[c] + li * br[c];
+        }
+    }
+#pragma unroll
+    for (int c = P - 1; c >= 0; --c) {
+        double sr = br[c], si = bi[c];
+#pragma unroll
+        for (int q = c + 1; q < P; ++q) {
+            sr -= ar[c][q] * br[q] - ai[c][q] * bi[q];
+            si -= ar[c][q] * bi[q] + ai[c][q] * br[q];
+        }
+        br[c] = sr * pr[c] - si * pi[c];
+        bi[c] = sr * pi[c] + si * pr[c];
+    }
+}
+
+template <int P>
+__device__ __forceinline__ void solve_real(double (&a)[P][P], double (&b)[P]) {
+    double p[P];
+#pragma unroll
+    for (int c = 0; c < P; ++c) {
+        p[c] = 1.0 / a[c][c];
+#pragma unroll
+        for (int r = c + 1; r < P; ++r) {
+            const double l = a[r][c] * p[c];
+#pragma unroll
+            for (int q = c + 1; q < P; ++q) a[r][q] -= l * a[c][q];
+            b[r] -= l * b[c];
+        }
+    }
+#pragma unroll
+    for (int c = P - 1; c >= 0; --c) {
+        double s = b[c];
+#pragma unroll
+        for (int q = c + 1; q < P; ++q) s -= a[c][q] * b[q];
+        b[c] = s * p[c];
+    }
+}
+
+template <int N, int NC, int P>
+__global__ void __launch_bounds__(Circ7Cfg<N, NC, P>::THREADS, 1)
+k_pc_circ(DevMesh m, const int32_t* __restrict__ cols, int sg, const double shift,
+          const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ circ_tab) {
+    using Cfg = Circ7Cfg<N, NC, P>;
+    constexpr int NN = Cfg::NN, NT = Cfg::NT, NTP = Cfg::NTP, SU = Cfg::SU, SW = Cfg::SW, M = Cfg::M;
+    constexpr int THREADS = Cfg::THREADS;
+    extern __shared__ __align__(16) double smem_pc[];
+    double* const U = smem_pc;
+    double* const W = smem_pc + Cfg::U_DOUBLES;
+    __shared__ double s_coef[2 * NN];
+    __shared__ double s_wt[P];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c = cols[blockIdx.x];
+    const int64_t off = m.col_slab_off[c];
+    for (int e = tid; e < NN * NT; e += THREADS) {
+        const int node = e / NT, th = e - node * NT;
+        U[node * SU + th] = x[off + (int64_t)node * NTP + th];
+    }
+    for (int e = tid; e < 2 * NN; e += THREADS) {
+        double v = m.coef[m.col_coef_off[c] + e];
+        if (e < NN) {                // mk = (dx dy / 4) w_i w_j kappa: floor kappa by shift / min(dx, dy)
+            const double dx = m.col_dx[c], dy = m.col_dy[c];
+            const double* wq = c_w + N * RT_MAXN;
+            v += shift * 0.25 * dx * dy * wq[e / N] * wq[e % N] / fmin(dx, dy);
+        }
+        s_coef[e] = v;
+    }
+    if (tid < P) s_wt[tid] = m.th_wt[m.sig_th0[sg] + tid];
+    __syncthreads();
+    fft_f7<Cfg>(U, W, warp, lane);
+    __syncthreads();
+    {
+        const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+        const bool on = lane < NN;
+        const int node = on ? lane : 0;
+        const double mk = s_coef[node], ms = s_coef[NN + node];
+        double2* const wn = reinterpret_cast<double2*>(W) + node * (SW / 2);
+        const double2* __restrict__ T = reinterpret_cast<const double2*>(circ_tab);
+        if (warp_u < Cfg::WORK_WARPS) {
+#pragma unroll 1
+            for (int k = warp_u; k < M; k += Cfg::WORK_WARPS) {
+                double2* const w2 = wn + k * P;
+                const double2* __restrict__ tk = T + k * P * P;
+                if (k == 0) {
+                    double a0[P][P], ah[P][P], b0[P], bh[P];
+#pragma unroll
+                    for (int r = 0; r < P; ++r) {
+                        const double2 b = w2[r];
+                        b0[r] = b.x;
+                        bh[r] = b.y;
+#pragma unroll
+                        for (int q = 0; q < P; ++q) {
+                            const double2 t = __ldg(&tk[r * P + q]);
+                            a0[r][q] = -(ms * (double)NC) * t.x + (r == q ? mk * s_wt[r] : 0.0);
+                            ah[r][q] = -(ms * (double)NC) * t.y + (r == q ? mk * s_wt[r] : 0.0);
+                        }
+                    }
+                    solve_real<P>(a0, b0);
+                    solve_real<P>(ah, bh);
+                    if (on) {
+#pragma unroll
+                        for (int r = 0; r < P; ++r) w2[r] = make_double2(b0[r], bh[r]);
+                    }
+                } else {
+                    double ar[P][P], ai[P][P], br[P], bi[P];
+#pragma unroll
+                    for (int r = 0; r < P; ++r) {
+                        const double2 b = w2[r];
+                        br[r] = 0.5 * b.x;
+                        bi[r] = 0.5 * b.y;
+#pragma unroll
+                        for (int q = 0; q < P; ++q) {
+                            const double2 t = __ldg(&tk[r * P + q]);
+                            ar[r][q] = -(ms * (2.0 * NC)) * t.x + (r == q ? mk * s_wt[r] : 0.0);
+                            ai[r][q] = -(ms * (2.0 * NC)) * t.y;
+                        }
+                    }
+                    solve_complex<P>(ar, ai, br, bi);
+                    if (on) {
+#pragma unroll
+                        for (int r = 0; r < P; ++r) w2[r] = make_double2(br[r], bi[r]);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    fft_i7<Cfg>(W, warp, lane);
+    __syncthreads();
+    for (int e = tid; e < NN * NTP; e += THREADS) {
+        const int node = e / NTP, th = e - node * NTP;
+        y[off + (int64_t)node * NTP + th] = th < NT ? W[node * SW + th] * (1.0 / NC) : 0.0;
+    }
+}
+
+template <int N, int NC, int P>
+static int launch_pc_circ(rtb200_ctx* ctx, const Bucket& b, const double* x, double* y, cudaStream_t st) {
+    if constexpr (NC >= 8) {
+        using Cfg = Circ7Cfg<N, NC, P>;
+        constexpr size_t smem = sizeof(double) * (size_t)(Cfg::U_DOUBLES + Cfg::W_DOUBLES);
+        auto kern = k_pc_circ<N, NC, P>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaFuncSetAttribute(k_pc_circ, smem)");
+        kern<<<b.count, Cfg::THREADS, smem, st>>>(ctx->dm, b.cols_dev, b.circ_sig, ctx->pc_shift, x, y,
+                                                  b.circ_tab_dev);
+        ctx->launches++;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return rt_cuda(ctx, e, "k_pc_circ launch");
+        return RTB200_OK;
+    } else {
+        return rt_fail(ctx, RTB200_EUNSUPPORTED, "block-Jacobi preconditioner needs >= 8 angular cells");
+    }
+}
+
+int rt_pc_setup(rtb200_ctx* ctx, cudaStream_t) {
+    if (!ctx->have_mesh) return rt_fail(ctx, RTB200_ESTATE, "no mesh set");
+    for (const Bucket& b : ctx->buckets)
+        if (b.circ_nc < 8)
+            return rt_fail(ctx, RTB200_EUNSUPPORTED,
+                           "the node-wise block-Jacobi preconditioner is built for uniform angular "
+                           "meshes (block-circulant scattering, >= 8 cells) only");
+    ctx->pc_ready = true;
+    return RTB200_OK;
+}
+
+int rt_pc_apply(rtb200_ctx* ctx, const double* x, double* y, cudaStream_t st) {
+    if (!ctx->pc_ready) {
+        int rc = rt_pc_setup(ctx, st);
+        if (rc) return rc;
+    }
+    for (const Bucket& b : ctx->buckets) {
+        int rc = RTB200_EUNSUPPORTED;
+#define X(N_, NC_, P_)                                               \
+    if (b.n == N_ && b.circ_nc == NC_ && b.circ_p == P_)             \
+        rc = launch_pc_circ<N_, NC_, P_>(ctx, b, x, y, st);
+        RT_CIRC_COMBOS(X)
+#undef X
+        if (rc) return rc == RTB200_EUNSUPPORTED ? rt_fail(ctx, rc, "preconditioner: unsupported bucket") : rc;
+    }
+    if (ctx->dm.n_col > 0) {
+        k_mask<<<ctx->dm.n_col, 256, 0, st>>>(ctx->dm, y, 1);
+        ctx->launches++;
+        RT_CUDA(ctx, cudaGetLastError());
+    }
+    return RTB200_OK;
+}
+
+void rt_pc_destroy(rtb200_ctx* ctx) { ctx->pc_ready = false; }
+
+extern "C" int rtb200_pc_set_shift(rtb200_ctx* ctx, double shift) {
+    if (!ctx) return RTB200_EINVAL;
+    if (!(shift >= 0.0)) return rt_fail(ctx, RTB200_EINVAL, "pc_set_shift: shift must be >= 0");
+    ctx->pc_shift = shift;
+    return RTB200_OK;
+}
+
+extern "C" int rtb200_pc_apply(rtb200_ctx* ctx, const double* x_slab_dev, double* y_slab_dev, void* stream) {
+    if (!ctx) return RTB200_EINVAL;
+    if (!ctx->have_mesh) return rt_fail(ctx, RTB200_ESTATE, "no mesh set (call rtb200_set_mesh first)");
+    if (!x_slab_dev || !y_slab_dev) return rt_fail(ctx, RTB200_EINVAL, "null device vector");
+    if (x_slab_dev == y_slab_dev) return rt_fail(ctx, RTB200_EINVAL, "pc_apply: x and y must not alias");
+    return rt_pc_apply(ctx, x_slab_dev, y_slab_dev, (cudaStream_t)stream);
+}

@@ -68,6 +68,7 @@ struct rtb200_ctx {
     double* pc_inv = nullptr;      // [sum over columns nn * ntp * ntp]
     int64_t* pc_off = nullptr;     // [n_col]
     bool pc_ready = false;
+    double pc_shift = 1.0;         // extinction floor of the preconditioner, in units of 1 / min(dx, dy)
 
     // halo / multi-GPU
     int rank = 0, nranks = 1;

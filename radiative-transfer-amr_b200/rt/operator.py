@@ -290,6 +290,19 @@ class RTOperator:
             return y
         return yd
 
+    def pc_apply(self, r_slab, z_slab=None):
+        """z = mask . (M - S)^{-1} r on slab-order device tensors: the node-wise
+        block-Jacobi preconditioner (inverse of the reference's ``preconditioner_matrix``,
+        uniform angular meshes only)."""
+        z_slab = self.empty_slab() if z_slab is None else z_slab
+        self._call("rtb200_pc_apply", self.lib.rtb200_pc_apply(
+            self.ctx, C.c_void_p(r_slab.data_ptr()), C.c_void_p(z_slab.data_ptr()), self._stream()))
+        return z_slab
+
+    def pc_set_shift(self, shift: float):
+        """Extinction floor of the preconditioner: kappa_eff = kappa + shift / min(dx, dy)."""
+        self._call("rtb200_pc_set_shift", self.lib.rtb200_pc_set_shift(self.ctx, float(shift)))
+
     def launch_count(self) -> int:
         return int(self.lib.rtb200_launch_count(self.ctx))
 
