@@ -50,6 +50,10 @@ WORKLOADS = {
     "c4-128": (7, 5, [5, 5, 5]),      # 6.55e7 DoF
     "c4-64": (6, 5, [5, 5, 5]),       # 1.64e7 DoF
     "c1": (2, 2, [4, 4, 4]),          # 4096 DoF (BASELINE configs[0] mesh)
+    # seeded synthetic hp-refined meshes (small twins of BASELINE configs[4]):
+    # (spatial base level, -, -); hanging nodes, degree jumps, non-uniform angular meshes
+    "c5-small": (6, None, None),      # ~3.7e6 DoF
+    "c5": (7, None, None),            # ~1.5e7 DoF
 }
 LS = [3.0, 2.0]
 BYTES_PER_DOF = 16.0                  # read x + write y, FP64
@@ -207,7 +211,7 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     ns, na, nd = WORKLOADS[args.workload]
-    arm = CpuArm(cores, (min(ns, 4), na, nd))
+    arm = CpuArm(cores, (min(ns, 4), na or 5, nd or [5, 5, 5]))
     for _ in range(max(args.warmup, 1)):
         arm.step()
     ts = [arm.step() for _ in range(args.steps)]
@@ -249,8 +253,11 @@ def run_b200(args):
     ns, na, nd = WORKLOADS[args.workload]
     prob = configs.two_strong_scatterers(LS)
     t0 = time.perf_counter()
-    arrays = MeshArrays.uniform(LS, ns, na, nd)
-    flat = FlatMesh(arrays, rank=rank, nranks=world)
+    if na is None:
+        hp_mesh = configs.hp_synthetic(LS, level=ns)
+        flat = FlatMesh(hp_mesh, rank=rank, nranks=world)
+    else:
+        flat = FlatMesh(MeshArrays.uniform(LS, ns, na, nd), rank=rank, nranks=world)
     op = RTOperator(flat, prob.kappa, prob.sigma, prob.Phi, device=dev)
     t_build = time.perf_counter() - t0
     if world > 1:
@@ -339,27 +346,64 @@ def run_b200(args):
     # ---- e2e: reference-facing call with host buffers ------------------- #
     e2e = None
     if not args.no_e2e:
+        # Every step: pinned host x (dof order) -> device, layout conversion, interior mask,
+        # apply, conversion back, device -> pinned host y.  On one GPU consecutive steps run
+        # on two streams with their own device buffers, so the H2D copy of step i + 1
+        # overlaps the D2H copy of step i (PCIe is full duplex); with several ranks the
+        # library's halo buffers are shared between applies, so steps stay on one stream.
+        nslot = 2 if world == 1 else 1
         xh = torch.empty(op.n, dtype=torch.float64).pin_memory()
         xh.normal_(generator=torch.Generator().manual_seed(7))
-        yh = torch.empty(op.n, dtype=torch.float64).pin_memory()
-        xd = torch.empty(op.n, dtype=torch.float64, device=dev)
-        yd = torch.empty(op.n, dtype=torch.float64, device=dev)
+        slots = []
+        for i in range(nslot):
+            slots.append({
+                "st": torch.cuda.Stream(device=dev) if nslot > 1 else torch.cuda.current_stream(dev),
+                "yh": torch.empty(op.n, dtype=torch.float64).pin_memory(),
+                "xd": torch.empty(op.n, dtype=torch.float64, device=dev),
+                "yd": torch.empty(op.n, dtype=torch.float64, device=dev),
+                "xs": x if i == 0 else op.empty_slab(), "ys": y if i == 0 else op.empty_slab()})
 
-        def e2e_step():
-            xd.copy_(xh, non_blocking=True)
-            op.to_slab(xd, x)
-            op.mask_slab(x, "interior")
-            op.apply_slab(x, y, 15, True)
-            op.from_slab(y, yd)
-            yh.copy_(yd, non_blocking=True)
+        def e2e_step(i):
+            sl = slots[i % nslot]
+            with torch.cuda.stream(sl["st"]):
+                sl["xd"].copy_(xh, non_blocking=True)
+                op.to_slab(sl["xd"], sl["xs"])
+                op.mask_slab(sl["xs"], "interior")
+                op.apply_slab(sl["xs"], sl["ys"], 15, True)
+                op.from_slab(sl["ys"], sl["yd"])
+                sl["yh"].copy_(sl["yd"], non_blocking=True)
 
-        e2e_step()
-        k = max(2, min(args.steps, 5))
-        ms_e2e = timed(e2e_step, k) / k
+        def e2e_run(k):
+            barrier()
+            main = torch.cuda.current_stream(dev)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(main)
+            for sl in slots:
+                sl["st"].wait_event(e0)
+            for i in range(k):
+                e2e_step(i)
+            for sl in slots:
+                if sl["st"] is not main:
+                    ev = torch.cuda.Event(); ev.record(sl["st"]); main.wait_event(ev)
+            e1.record(main)
+            barrier()
+            ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return float(ms.item())
+
+        e2e_run(2)
+        k = max(4, min(args.steps, 8))
+        ms_e2e = e2e_run(k) / k
+        # the last result really is on the host and equals the resident-input result
+        op.apply_slab(op.mask_slab(op.to_slab(xh.to(dev)), "interior"), y, 15, True)
+        chk = float((op.from_slab(y).cpu() - slots[(k - 1) % nslot]["yh"]).abs().max())
         e2e = {"value": n_total / ms_e2e / 1e6, "unit": "GDoF/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(op.n * 8), "d2h_bytes_per_step": int(op.n * 8),
-               "call": "to_slab + mask + apply + from_slab on pinned host vectors in dof order"}
-        del xh, yh, xd, yd
+               "streams": nslot, "max_abs_diff_vs_resident": chk,
+               "call": "RTOperator.to_slab + mask_slab + apply_slab + from_slab on pinned host "
+                       "vectors in dof order (H2D and D2H copies inside the timed region)"}
+        del xh, slots
 
     # ---- GMRES Arnoldi timing on the same mesh --------------------------- #
     gm = None
@@ -396,7 +440,7 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        r = cpu_reference_arm(1, (min(ns, 4), na, nd), reps=5)
+        r = cpu_reference_arm(1, (min(ns, 4), na or 5, nd or [5, 5, 5]), reps=5)
         cpu = {"value": r["n"] / r["t_apply_s"] / 1e9, "unit": "GDoF/s", "cores": 1,
                "kind": "port", "sample": r["sample"], "assemble_s": r["t_assemble_s"],
                "host_cores_available": cores}
@@ -407,8 +451,12 @@ def run_b200(args):
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": args.workload,
-                           "mesh": "uniform %dx%d columns x %d angular cells, ndofs %s"
-                                   % (2 ** ns, 2 ** ns, 2 ** na, nd),
+                           "mesh": ("uniform %dx%d columns x %d angular cells, ndofs %s"
+                                    % (2 ** ns, 2 ** ns, 2 ** na, nd)) if na is not None else
+                                   ("seeded hp-refined mesh from a uniform %dx%d base: %d columns, "
+                                    "%d angular signatures (configs.hp_synthetic)"
+                                    % (2 ** ns, 2 ** ns, flat.n_col_global if hasattr(flat, "n_col_global")
+                                       else flat.n_col, len(flat.sig_nt))),
                            "ndof": int(n_total), "terms": "BC - IC + M - S, interior rows",
                            "coefficients": "two-strong-scatterers kappa/sigma, HG g=0.8",
                            "partition": "np.array_split of sorted column keys over %d rank(s)" % world,

@@ -41,6 +41,40 @@ def build_mesh(Ls, pbcs, ndofs, nref_ang, nref_spt, has_th=True, **_) -> Mesh:
     return mesh
 
 
+def hp_synthetic(Ls=(3.0, 2.0), level: int = 4, seed: int = 20240817, ndofs=(3, 3, 3),
+                 frac_h: float = 0.3, frac_p: float = 0.35, frac_ang: float = 0.3) -> Mesh:
+    """Seeded synthetic hp-refined mesh (a small twin of BASELINE.json configs[4], built
+    with the same ``Mesh.ref_col`` / ``ref_cell`` calls the reference's AMR loop issues, so
+    2:1 balance and degree-jump rules are the reference's own): uniform spatial level
+    ``level`` with 8 angular cells, then a random ``frac_h`` of the columns h-refined in
+    space, ``frac_p`` of the columns p-refined in space (twice for a third of them), and
+    in a random ``frac_ang`` of the columns some angular cells h- or p-refined.  The result
+    has hanging nodes, spatial degree jumps and non-uniform angular meshes (dense
+    scattering path) next to untouched columns (block-circulant path)."""
+    rng = np.random.default_rng(seed)
+    mesh = build_mesh(Ls, [False, False], list(ndofs), nref_ang=3, nref_spt=level)
+    keys = sorted(mesh.cols.keys())
+    for k in rng.choice(keys, size=int(frac_h * len(keys)), replace=False):
+        if int(k) in mesh.cols:
+            mesh.ref_col(int(k), kind="spt", form="h")
+    keys = sorted(mesh.cols.keys())
+    for n, k in enumerate(rng.choice(keys, size=int(frac_p * len(keys)), replace=False)):
+        if int(k) in mesh.cols:
+            mesh.ref_col(int(k), kind="spt", form="p")
+            if n % 3 == 0 and int(k) in mesh.cols:
+                mesh.ref_col(int(k), kind="spt", form="p")
+    keys = sorted(mesh.cols.keys())
+    for k in rng.choice(keys, size=int(frac_ang * len(keys)), replace=False):
+        col = mesh.cols.get(int(k))
+        if col is None:
+            continue
+        cks = sorted(col.cells.keys())
+        for ck in rng.choice(cks, size=max(1, len(cks) // 4), replace=False):
+            if int(ck) in mesh.cols[int(k)].cells:
+                mesh.ref_cell(int(k), int(ck), form="h" if rng.random() < 0.5 else "p")
+    return mesh
+
+
 def _hg_phase(g: float):
     """Normalised Henyey-Greenstein-type phase function used by the scatterer
     experiments (``two-strong-scatterers/problem.py:36-43``)."""

@@ -109,3 +109,29 @@ def test_error_paths(torch_cuda):
     assert rc == -3 and b"mesh" in lib.rtb200_last_error(ctx)
     assert lib.rtb200_create(10_000, C.byref(C.c_void_p())) != 0
     lib.rtb200_destroy(ctx)
+
+
+@pytest.mark.parametrize("level", [2, 3])
+def test_seeded_hp_synthetic_mesh_matches_oracle(level):
+    """Small twins of the hp-refined benchmark mesh (configs.hp_synthetic: hanging nodes,
+    spatial degree jumps, angular h/p refinement next to untouched uniform columns, i.e.
+    the dense, the one-block-per-column and the persistent circulant kernels in one apply)."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    from oracle import rt_oracle as O
+    from rt_b200 import configs
+    from rt_b200.rt import RTOperator
+    prob = configs.two_strong_scatterers()
+    mesh = configs.hp_synthetic(level=level)
+    op = RTOperator(mesh, prob.kappa, prob.sigma, prob.Phi)
+    ref = O.assemble(mesh, prob.kappa, prob.sigma, prob.Phi)
+    x = np.random.default_rng(3).standard_normal(op.n)
+    for terms, key, sign in ((3, "MS", 1.0), (4, "IC", -1.0), (8, "BC", 1.0), (15, "A", 1.0)):
+        y = op.mult(x, terms=terms)
+        yr = sign * (ref[key] @ x)            # A = BC - IC + (M - S)
+        assert rel_err(y, yr) <= 1e-11, (terms, rel_err(y, yr))
+    mask = ref["mask"].astype(bool)
+    yi = op.mult(x * mask, interior_only=True)
+    assert rel_err(yi[mask], (ref["A"] @ (x * mask))[mask]) <= 1e-11
+    assert np.all(yi[~mask] == 0.0)
