@@ -350,7 +350,10 @@ static int launch_circ(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int int
             e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared);
             if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaFuncSetAttribute(k_apply_circ7, carveout)");
-            const int grid = std::min(b.count, 2 * ctx->sm_count);
+            int per_sm = 2;                       // persistent grid: every block the SMs can hold
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::THREADS, Cfg::SMEM);
+            if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+            const int grid = std::min(b.count, std::max(per_sm, 1) * ctx->sm_count);
             if (b.circ_tab_host.size() != sizeof(CircTab7<Cfg>) / sizeof(double))
                 return rt_fail(ctx, RTB200_EINVAL, "circulant table size mismatch");
             CircTab7<Cfg> T;                      // 16 M P^2 bytes, passed in the constant bank
@@ -379,32 +382,61 @@ static int launch_circ(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int int
     return RTB200_OK;
 }
 
-int rt_launch_apply(rtb200_ctx* ctx, unsigned terms, int interior_only, const double* x,
-                    double* y, cudaStream_t st) {
-    for (const Bucket& b : ctx->buckets) {
-        int rc = RTB200_EUNSUPPORTED;
-        if (b.circ_nc > 0) {
+static int launch_one_bucket(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int interior_only,
+                             const double* x, double* y, cudaStream_t st) {
+    int rc = RTB200_EUNSUPPORTED;
+    if (b.circ_nc > 0) {
 #define X(N_, NC_, P_)                                                                  \
     if (b.n == N_ && b.circ_nc == NC_ && b.circ_p == P_)                                \
         rc = launch_circ<N_, NC_, P_>(ctx, b, terms, interior_only, x, y, st);
-            RT_CIRC_COMBOS(X)
+        RT_CIRC_COMBOS(X)
 #undef X
-            if (rc) return rc;
-            continue;
-        }
-        switch (b.n) {
-            case 2: rc = launch_bucket<2>(ctx, b, terms, interior_only, x, y, st); break;
-            case 3: rc = launch_bucket<3>(ctx, b, terms, interior_only, x, y, st); break;
-            case 4: rc = launch_bucket<4>(ctx, b, terms, interior_only, x, y, st); break;
-            case 5: rc = launch_bucket<5>(ctx, b, terms, interior_only, x, y, st); break;
-            case 6: rc = launch_bucket<6>(ctx, b, terms, interior_only, x, y, st); break;
-            case 7: rc = launch_bucket<7>(ctx, b, terms, interior_only, x, y, st); break;
-            case 8: rc = launch_bucket<8>(ctx, b, terms, interior_only, x, y, st); break;
-            default: rc = launch_bucket<0>(ctx, b, terms, interior_only, x, y, st); break;
-        }
-        if (rc) return rc;
+        return rc;
     }
-    return RTB200_OK;
+    switch (b.n) {
+        case 2: rc = launch_bucket<2>(ctx, b, terms, interior_only, x, y, st); break;
+        case 3: rc = launch_bucket<3>(ctx, b, terms, interior_only, x, y, st); break;
+        case 4: rc = launch_bucket<4>(ctx, b, terms, interior_only, x, y, st); break;
+        case 5: rc = launch_bucket<5>(ctx, b, terms, interior_only, x, y, st); break;
+        case 6: rc = launch_bucket<6>(ctx, b, terms, interior_only, x, y, st); break;
+        case 7: rc = launch_bucket<7>(ctx, b, terms, interior_only, x, y, st); break;
+        case 8: rc = launch_bucket<8>(ctx, b, terms, interior_only, x, y, st); break;
+        default: rc = launch_bucket<0>(ctx, b, terms, interior_only, x, y, st); break;
+    }
+    return rc;
+}
+
+// The buckets of an hp mesh (one per compile-time size and kernel family) read the same x
+// and write disjoint slabs of y, and most of them are too small to fill the GPU: they are
+// launched on a few side streams forked from / joined to the caller's stream, largest
+// bucket first, so that their tails overlap instead of adding up.
+int rt_launch_apply(rtb200_ctx* ctx, unsigned terms, int interior_only, const double* x,
+                    double* y, cudaStream_t st) {
+    const size_t nb = ctx->buckets.size();
+    if (nb <= 1 || ctx->side_streams.empty()) {
+        for (const Bucket& b : ctx->buckets) {
+            int rc = launch_one_bucket(ctx, b, terms, interior_only, x, y, st);
+            if (rc) return rc;
+        }
+        return RTB200_OK;
+    }
+    const size_t ns = ctx->side_streams.size();
+    RT_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+    for (size_t s = 0; s < std::min(ns, nb - 1); ++s)
+        RT_CUDA(ctx, cudaStreamWaitEvent(ctx->side_streams[s], ctx->ev_fork, 0));
+    int rc = RTB200_OK;
+    for (size_t i = 0; i < nb && rc == RTB200_OK; ++i) {
+        const Bucket& b = ctx->buckets[ctx->bucket_order[i]];
+        // slot 0 is the caller's stream, slots 1.. the side streams
+        const size_t slot = i % (std::min(ns, nb - 1) + 1);
+        rc = launch_one_bucket(ctx, b, terms, interior_only, x, y,
+                               slot == 0 ? st : ctx->side_streams[slot - 1]);
+    }
+    for (size_t s = 0; s < std::min(ns, nb - 1); ++s) {      // always join, also after an error
+        cudaEventRecord(ctx->ev_join[s], ctx->side_streams[s]);
+        cudaStreamWaitEvent(st, ctx->ev_join[s], 0);
+    }
+    return rc;
 }
 
 int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
@@ -512,6 +544,26 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
         if ((rc = up(a.first, &b.grp_first_dev))) return rc;
         if ((rc = up(a.count, &b.grp_count_dev))) return rc;
         ctx->buckets.push_back(b);
+    }
+    // launch order: most columns x angles first
+    ctx->bucket_order.resize(ctx->buckets.size());
+    for (size_t i = 0; i < ctx->buckets.size(); ++i) ctx->bucket_order[i] = (int)i;
+    std::sort(ctx->bucket_order.begin(), ctx->bucket_order.end(), [&](int a, int b) {
+        const Bucket &A = ctx->buckets[a], &B = ctx->buckets[b];
+        return (int64_t)A.count * A.max_ntp * std::max(A.n, 1) * std::max(A.n, 1) >
+               (int64_t)B.count * B.max_ntp * std::max(B.n, 1) * std::max(B.n, 1);
+    });
+    if (ctx->buckets.size() > 1 && ctx->side_streams.empty()) {
+        constexpr int NSIDE = 5;
+        for (int s = 0; s < NSIDE; ++s) {
+            cudaStream_t q;
+            cudaEvent_t ev;
+            RT_CUDA(ctx, cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+            ctx->side_streams.push_back(q);
+            RT_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            ctx->ev_join.push_back(ev);
+        }
+        RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     }
     return RTB200_OK;
 }

@@ -73,6 +73,9 @@ struct Circ7Cfg {
     static constexpr size_t SMEM = sizeof(double) * (size_t)(2 * U_DOUBLES + W_DOUBLES + T_DOUBLES +
                                                              TAB_DOUBLES + 2 * COEF_DOUBLES);
     static constexpr int NA = (NN + 1) / 2;                    // nodes [0, NA) -> half 0, rest -> half 1
+    // resident blocks per SM the register allocation aims at: 2 at the benchmark size (320
+    // threads, 96 registers), more for the small blocks of low-order / few-cell columns
+    static constexpr int MINB = 640 / THREADS < 2 ? 2 : (640 / THREADS > 8 ? 8 : 640 / THREADS);
     static_assert(NW_MAX * P <= 16, "a warp transforms at most 16 sequences");
 };
 
@@ -514,7 +517,7 @@ __device__ __noinline__ void fft_i7(double* __restrict__ W, const int warp, cons
 }
 
 template <int N, int NC, int P>
-__global__ void __launch_bounds__(Circ7Cfg<N, NC, P>::THREADS, RT7_MINB)
+__global__ void __launch_bounds__(Circ7Cfg<N, NC, P>::THREADS, Circ7Cfg<N, NC, P>::MINB)
 k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int sg, unsigned terms,
               int interior_only, const double* __restrict__ x, const double* __restrict__ ghost,
               double* __restrict__ y, const __grid_constant__ CircTab7<Circ7Cfg<N, NC, P>> T) {

@@ -59,6 +59,12 @@ extern "C" void rtb200_destroy(rtb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     free_tables(ctx);
+    for (cudaStream_t q : ctx->side_streams) cudaStreamDestroy(q);
+    for (cudaEvent_t e : ctx->ev_join) cudaEventDestroy(e);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    ctx->side_streams.clear();
+    ctx->ev_join.clear();
+    ctx->ev_fork = nullptr;
     rt_comm_destroy(ctx);
     delete ctx;
 }

@@ -56,6 +56,10 @@ struct rtb200_ctx {
     DevMesh dm{};
     std::vector<void*> allocs; // private device allocations (tables)
     std::vector<Bucket> buckets;
+    std::vector<int> bucket_order;              // launch order (largest first)
+    std::vector<cudaStream_t> side_streams;     // buckets of an hp mesh run concurrently
+    std::vector<cudaEvent_t> ev_join;
+    cudaEvent_t ev_fork = nullptr;
     double* coef_dev = nullptr;
     int64_t n_coef = 0;
     const double* circ_pool_dev = nullptr;
