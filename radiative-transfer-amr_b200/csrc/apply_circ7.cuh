@@ -1,31 +1,32 @@
 // Persistent, prefetching apply kernel for columns with a UNIFORM angular mesh
 // (NC >= 8 equal cells of P nodes; block-circulant scattering, see apply_circ.cuh
-// for the algorithm and the table conventions).
+// for the algorithm and the table conventions) whose faces are all conforming
+// (columns with a mortar face are routed to k_apply_circ by the host).
 //
 // What changed against k_apply_circ (one block per column, phases in lock step):
-//   * persistent blocks (2 per SM) walk the column list with a grid stride and
-//     PREFETCH the next column's slab + coefficients with cp.async into a second
-//     buffer while the current column is being processed: the HBM stream and the
-//     FP64 phases overlap by construction instead of by luck of block scheduling;
+//   * persistent blocks (as many as the SMs hold: 2 per SM at the benchmark size) walk
+//     the column list with a grid stride and PREFETCH the next column's slab +
+//     coefficient samples with bulk asynchronous copies (cp.async.bulk, one per slab
+//     row, completing on an mbarrier) into a second buffer while the current column is
+//     processed: the HBM stream and the FP64 phases overlap by construction;
 //   * twice the threads per column at <= 96 registers: every length-NC real FFT is
 //     split over the two lanes (l, l ^ 16) of a warp -- each transforms the even or
 //     the odd samples (length NC/2, in registers), the last radix-2 stage swaps NC/4
 //     doubles with shuffles -- and the streaming terms of an angle are split over
 //     two threads (first / second half of the spatial nodes);
-//   * block product: a 5-lane group owns one (frequency slot, node) item at a time
-//     and walks a contiguous, evenly sized range of the NC/2 x NN items, next
-//     item's operands in flight while the current one is multiplied (4 chains);
-//   * the per-angle tables (weights, cos, sin, face weights, upwind bits) are
-//     staged in shared memory once per block; column metadata runs two columns
-//     ahead in a 3-slot ring.
+//   * a warp owns whole spatial nodes in the FFT phases (the inverse transform writes
+//     its rows in place with only a __syncwarp); the block product runs with one lane
+//     per node and a warp-uniform frequency slot, two slots interleaved;
+//   * the last warp is the producer (bulk copies, column metadata two columns ahead in
+//     a 3-slot ring) and stays out of the FFT / block-product phases;
+//   * per-angle tables (weights, wt cos, wt sin, upwind bits) and the block spectrum
+//     are staged in shared memory once per block.
 //
-// Shared memory per block at (N, NC, P) = (5, 32, 5): 2 x 33.0 KB (U) + 34.0 KB (W)
-// + 6.4 KB (block spectrum) + 4.5 KB (angle tables) + 0.8 KB = 111.7 KB -> 2 blocks / SM.
+// Shared memory per block at (N, NC, P) = (5, 32, 5): 2 x 33.2 KB (U) + 34.0 KB (W)
+// + 6.4 KB (block spectrum) + 4.5 KB (angle tables) + 0.8 KB = 112.1 KB -> 2 blocks / SM.
+// Measurements and what bounds the kernel: DESIGN.md 4.1, profiles/r01_v13_summary.md.
 #pragma once
 #include <utility>
-#ifndef RT7_MINB
-#define RT7_MINB 2
-#endif
 
 template <int N_, int NC_, int P_>
 struct Circ7Cfg {
