@@ -359,7 +359,8 @@ static int launch_circ(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int int
             CircTab7<Cfg> T;                      // 16 M P^2 bytes, passed in the constant bank
             memcpy(&T, b.circ_tab_host.data(), sizeof(T));
             kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(ctx->dm, b.cols_dev, b.count, b.circ_sig, terms,
-                                                        interior_only, x, ctx->ghost_dev, y, T);
+                                                        interior_only, b.circ_herm ? 1 : 0, x,
+                                                        ctx->ghost_dev, y, T);
             ctx->launches++;
             e = cudaGetLastError();
             if (e != cudaSuccess) return rt_cuda(ctx, e, "k_apply_circ7 launch");
@@ -527,6 +528,21 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
             b.circ_tab_dev = ctx->circ_pool_dev + m->sig_circ_off[sig];
             const double* th = m->circ_pool + m->sig_circ_off[sig];
             b.circ_tab_host.assign(th, th + (size_t)(b.circ_nc / 2) * b.circ_p * b.circ_p * 2);
+            {   // Hermitian block spectrum?  (slot 0 packs two real matrices: both symmetric)
+                const int P = b.circ_p, M = b.circ_nc / 2;
+                double tmax = 0.0, dmax = 0.0;
+                for (int k = 0; k < M; ++k)
+                    for (int r = 0; r < P; ++r)
+                        for (int q = 0; q < P; ++q) {
+                            const double* t = th + 2 * ((size_t)(k * P + r) * P + q);
+                            const double* u = th + 2 * ((size_t)(k * P + q) * P + r);
+                            tmax = std::max(tmax, std::max(std::fabs(t[0]), std::fabs(t[1])));
+                            dmax = std::max(dmax, std::fabs(t[0] - u[0]));
+                            dmax = std::max(dmax, k == 0 ? std::fabs(t[1] - u[1]) : std::fabs(t[1] + u[1]));
+                        }
+                const char* env = getenv("RTB200_CIRC_HERMITIAN");
+                b.circ_herm = dmax <= 1e-13 * tmax && !(env && env[0] == '0');
+            }
         } else {
             b.ntps = ntps_for(b.max_ntp);
             b.smem = sizeof(double) * a.rows_max * (size_t)b.ntps;

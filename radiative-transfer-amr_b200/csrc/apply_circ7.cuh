@@ -486,6 +486,83 @@ __device__ __noinline__ void mult7(double* __restrict__ W, const double2* __rest
     if (k < M) mult7_one<Cfg>(wn + k * P, Ts + k * P * P, on);
 }
 
+// Same product when every block T[k] is Hermitian (scattering kernels that are symmetric
+// in (theta, theta'), e.g. any Phi(|theta - theta'|): G = diag(wt) Phi diag(wt) is then
+// symmetric and its block spectrum Hermitian; checked numerically on the host).  Only the
+// upper triangle is read: T[r][q] feeds y[r] += T[r][q] u[q] and y[q] += conj(T[r][q]) u[r],
+// 15 instead of 25 broadcast loads per slot, all P outputs accumulated at once (4 P
+// independent chains, so slots are not paired).
+template <typename Cfg>
+__device__ __noinline__ void mult7_herm(double* __restrict__ W, const double2* __restrict__ Ts,
+                                        const int warp_u, const int lane) {
+    constexpr int P = Cfg::P, NN = Cfg::NN, SW = Cfg::SW, M = Cfg::M, WW = Cfg::WORK_WARPS;
+    static_assert(NN <= 32, "one lane per spatial node");
+    if (warp_u >= WW) return;
+    const bool on = lane < NN;
+    double2* const wn = reinterpret_cast<double2*>(W) + (on ? lane : 0) * (SW / 2);
+#pragma unroll 1
+    for (int k = warp_u; k < M; k += WW) {
+        double2* const w2 = wn + k * P;
+        const double2* __restrict__ tk = Ts + k * P * P;
+        double2 u[P];
+#pragma unroll
+        for (int q = 0; q < P; ++q) u[q] = w2[q];
+        if (k == 0) {            // two real symmetric products: re <- T.x u.x, im <- T.y u.y
+            double yr[P], yi[P];
+#pragma unroll
+            for (int r = 0; r < P; ++r) {
+                const double2 t = tk[r * P + r];
+                yr[r] = t.x * u[r].x;
+                yi[r] = t.y * u[r].y;
+            }
+#pragma unroll
+            for (int r = 0; r < P; ++r)
+#pragma unroll
+                for (int q = r + 1; q < P; ++q) {
+                    const double2 t = tk[r * P + q];
+                    yr[r] = fma(t.x, u[q].x, yr[r]);
+                    yi[r] = fma(t.y, u[q].y, yi[r]);
+                    yr[q] = fma(t.x, u[r].x, yr[q]);
+                    yi[q] = fma(t.y, u[r].y, yi[q]);
+                }
+            if (on) {
+#pragma unroll
+                for (int r = 0; r < P; ++r) w2[r] = make_double2(yr[r], yi[r]);
+            }
+        } else {
+            double y0[P], y1[P], y2[P], y3[P];       // re = y0 - y1, im = y2 + y3
+#pragma unroll
+            for (int r = 0; r < P; ++r) {
+                const double2 t = tk[r * P + r];
+                y0[r] = t.x * u[r].x;
+                y1[r] = t.y * u[r].y;
+                y2[r] = t.x * u[r].y;
+                y3[r] = t.y * u[r].x;
+            }
+#pragma unroll
+            for (int r = 0; r < P; ++r)
+#pragma unroll
+                for (int q = r + 1; q < P; ++q) {
+                    const double2 t = tk[r * P + q];
+                    // y[r] += t u[q]
+                    y0[r] = fma(t.x, u[q].x, y0[r]);
+                    y1[r] = fma(t.y, u[q].y, y1[r]);
+                    y2[r] = fma(t.x, u[q].y, y2[r]);
+                    y3[r] = fma(t.y, u[q].x, y3[r]);
+                    // y[q] += conj(t) u[r]
+                    y0[q] = fma(t.x, u[r].x, y0[q]);
+                    y1[q] = fma(-t.y, u[r].y, y1[q]);
+                    y2[q] = fma(t.x, u[r].y, y2[q]);
+                    y3[q] = fma(-t.y, u[r].x, y3[q]);
+                }
+            if (on) {
+#pragma unroll
+                for (int r = 0; r < P; ++r) w2[r] = make_double2(y0[r] - y1[r], y2[r] + y3[r]);
+            }
+        }
+    }
+}
+
 template <typename Cfg>
 __device__ __noinline__ void fft_i7(double* __restrict__ W, const int warp, const int lane) {
     constexpr int NC = Cfg::NC, P = Cfg::P, H = Cfg::H, NP = NC / 8, SW = Cfg::SW;
@@ -520,7 +597,7 @@ __device__ __noinline__ void fft_i7(double* __restrict__ W, const int warp, cons
 template <int N, int NC, int P>
 __global__ void __launch_bounds__(Circ7Cfg<N, NC, P>::THREADS, Circ7Cfg<N, NC, P>::MINB)
 k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int sg, unsigned terms,
-              int interior_only, const double* __restrict__ x, const double* __restrict__ ghost,
+              int interior_only, int herm, const double* __restrict__ x, const double* __restrict__ ghost,
               double* __restrict__ y, const __grid_constant__ CircTab7<Circ7Cfg<N, NC, P>> T) {
     using Cfg = Circ7Cfg<N, NC, P>;
     constexpr int NN = Cfg::NN, NT = Cfg::NT, NTP = Cfg::NTP;
@@ -597,7 +674,10 @@ k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int 
         if (terms & RTB200_TERM_SCAT) {
             fft_f7<Cfg>(U, W, warp, lane);
             __syncthreads();
-            mult7<Cfg>(W, reinterpret_cast<const double2*>(Ts), __shfl_sync(0xffffffffu, warp, 0), lane);
+            if (herm)
+                mult7_herm<Cfg>(W, reinterpret_cast<const double2*>(Ts), __shfl_sync(0xffffffffu, warp, 0), lane);
+            else
+                mult7<Cfg>(W, reinterpret_cast<const double2*>(Ts), __shfl_sync(0xffffffffu, warp, 0), lane);
             __syncthreads();
             fft_i7<Cfg>(W, warp, lane);
             __syncthreads();

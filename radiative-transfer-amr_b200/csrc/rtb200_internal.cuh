@@ -42,6 +42,7 @@ struct Bucket {
     int32_t* grp_count_dev = nullptr;   // [n_groups] columns in the group
     // block-circulant scattering (uniform angular mesh): NC cells of P nodes; 0 = dense
     int circ_nc = 0, circ_p = 0, circ_sig = 0;
+    bool circ_herm = false;             // every block of the spectrum is Hermitian (symmetric Phi)
     bool circ_conforming = false;       // no mortar face in any column of the bucket
     const double* circ_tab_dev = nullptr;
     std::vector<double> circ_tab_host;  // same table, host copy (kernel parameter of k_apply_circ7)
