@@ -74,8 +74,10 @@ struct GroupTab {
 #include "apply_circ.cuh"
 #include "apply_circ7.cuh"
 
-template <int N>
-__global__ void __launch_bounds__(AP_THREADS, 2)
+// TH threads per block: 256, or 128 for buckets of short rows (<= 64 angles: few n-tiles
+// and few (column, angle) items, so half the warps of a 256-thread block would idle)
+template <int N, int TH>
+__global__ void __launch_bounds__(TH, 512 / TH)
 k_apply(DevMesh m, GroupTab gt, unsigned terms, int interior_only, const double* __restrict__ x,
         const double* __restrict__ ghost, double* __restrict__ y, int ntps) {
     extern __shared__ __align__(16) double u_s[];
@@ -100,14 +102,14 @@ k_apply(DevMesh m, GroupTab gt, unsigned terms, int interior_only, const double*
     {
         const int chunks = ntp >> 1;                       // 16-byte chunks per row
         const int total = M * chunks;
-        for (int e = threadIdx.x; e < total; e += AP_THREADS) {
+        for (int e = threadIdx.x; e < total; e += TH) {
             const int row = e / chunks, ch = e - row * chunks;
             const int cg = row / nn, n = row - cg * nn;
             cp_async16(&u_s[row * ntps + 2 * ch],
                        x + m.col_slab_off[s_col[cg]] + (int64_t)n * ntp + 2 * ch);
         }
         const int padc = ntps - ntp;                       // zero the pad columns
-        for (int e = threadIdx.x; e < M * padc; e += AP_THREADS) {
+        for (int e = threadIdx.x; e < M * padc; e += TH) {
             const int row = e / padc, k = e - row * padc;
             u_s[row * ntps + ntp + k] = 0.0;
         }
@@ -117,7 +119,7 @@ k_apply(DevMesh m, GroupTab gt, unsigned terms, int interior_only, const double*
 
     // ---- phase 1: streaming terms, one thread per (column, theta) ------------ //
     if (terms & (RTB200_TERM_MASS | RTB200_TERM_ICONV | RTB200_TERM_BCONV)) {
-        for (int item = threadIdx.x; item < cg_n * ntp; item += AP_THREADS) {
+        for (int item = threadIdx.x; item < cg_n * ntp; item += TH) {
             const int cg = item / ntp, th = item - cg * ntp;
             const int c = s_col[cg];
             if (th >= nt) {
@@ -147,18 +149,18 @@ k_apply(DevMesh m, GroupTab gt, unsigned terms, int interior_only, const double*
 
         for (int mc = 0; mc < m_tiles; mc += AP_MT) {              // chunks of <= 64 rows
             const int mt_n = min(AP_MT, m_tiles - mc);
-            for (int nb = warp; nb < n_tiles; nb += AP_WARPS * AP_NTB) {   // passes over my n-tiles
+            for (int nb = warp; nb < n_tiles; nb += (TH / 32) * AP_NTB) {   // passes over my n-tiles
                 double acc[AP_MT][AP_NTB][2];
 #pragma unroll
                 for (int a = 0; a < AP_MT; ++a)
 #pragma unroll
                     for (int b = 0; b < AP_NTB; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-                const int nbv = min(AP_NTB, (n_tiles - nb + AP_WARPS - 1) / AP_WARPS);   // my tiles this pass
+                const int nbv = min(AP_NTB, (n_tiles - nb + (TH / 32) - 1) / (TH / 32));   // my tiles this pass
                 const double2* gp[AP_NTB];
 #pragma unroll
                 for (int b = 0; b < AP_NTB; ++b) {
-                    const int ntile = min(nb + b * AP_WARPS, n_tiles - 1);
+                    const int ntile = min(nb + b * (TH / 32), n_tiles - 1);
                     gp[b] = reinterpret_cast<const double2*>(G + (int64_t)(ntile * 8 + lr) * k8 + 2 * lk);
                 }
                 const double* ap = u_s + (mc * 8 + lr) * ntps + 2 * lk;
@@ -201,7 +203,7 @@ k_apply(DevMesh m, GroupTab gt, unsigned terms, int interior_only, const double*
                     double* yr = y + m.col_slab_off[c] + (int64_t)n * ntp;
 #pragma unroll
                     for (int b = 0; b < AP_NTB; ++b) {
-                        const int ntile = nb + b * AP_WARPS;
+                        const int ntile = nb + b * (TH / 32);
                         const int th = ntile * 8 + 2 * lk;
                         if (ntile >= n_tiles || th >= ntp) continue;
                         double2 v = first_write ? make_double2(0.0, 0.0)
@@ -306,14 +308,15 @@ static int ntps_for(int ntp) {
 template <int N>
 static int launch_bucket(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int interior_only,
                          const double* x, double* y, cudaStream_t st) {
-    auto kern = k_apply<N>;
+    const bool small = b.max_ntp <= 64;
+    auto kern = small ? k_apply<N, 128> : k_apply<N, 256>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.smem);
     if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaFuncSetAttribute(k_apply, smem)");
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaFuncSetAttribute(k_apply, carveout)");
     GroupTab gt{b.grp_first_dev, b.grp_count_dev, b.cols_dev};
-    kern<<<b.n_groups, AP_THREADS, b.smem, st>>>(ctx->dm, gt, terms, interior_only, x,
+    kern<<<b.n_groups, small ? 128 : 256, b.smem, st>>>(ctx->dm, gt, terms, interior_only, x,
                                                  ctx->ghost_dev, y, b.ntps);
     ctx->launches++;
     e = cudaGetLastError();
