@@ -340,7 +340,10 @@ static bool circ_supported(int n, int nc, int p) {
 
 template <int N, int NC, int P>
 static int launch_circ(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int interior_only,
-                       const double* x, double* y, cudaStream_t st) {
+                       const double* x, double* y, cudaStream_t st,
+                       const int32_t* cols_dev = nullptr, int count = -1) {
+    if (count < 0) { cols_dev = b.cols_dev; count = b.count; }
+    if (count == 0) return RTB200_OK;
     cudaError_t e;
     if constexpr (NC >= 8) {
         // persistent, prefetching kernel (apply_circ7.cuh): 2 blocks per SM walk the column list
@@ -356,12 +359,12 @@ static int launch_circ(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int int
             int per_sm = 2;                       // persistent grid: every block the SMs can hold
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::THREADS, Cfg::SMEM);
             if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-            const int grid = std::min(b.count, std::max(per_sm, 1) * ctx->sm_count);
+            const int grid = std::min(count, std::max(per_sm, 1) * ctx->sm_count);
             if (b.circ_tab_host.size() != sizeof(CircTab7<Cfg>) / sizeof(double))
                 return rt_fail(ctx, RTB200_EINVAL, "circulant table size mismatch");
             CircTab7<Cfg> T;                      // 16 M P^2 bytes, passed in the constant bank
             memcpy(&T, b.circ_tab_host.data(), sizeof(T));
-            kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(ctx->dm, b.cols_dev, b.count, b.circ_sig, terms,
+            kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(ctx->dm, cols_dev, count, b.circ_sig, terms,
                                                         interior_only, b.circ_herm ? 1 : 0, x,
                                                         ctx->ghost_dev, y, T);
             ctx->launches++;
@@ -377,7 +380,7 @@ static int launch_circ(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int int
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaFuncSetAttribute(k_apply_circ, carveout)");
-    kern<<<b.count, Cfg::THREADS, Cfg::SMEM, st>>>(ctx->dm, b.cols_dev, b.circ_sig, terms,
+    kern<<<count, Cfg::THREADS, Cfg::SMEM, st>>>(ctx->dm, cols_dev, b.circ_sig, terms,
                                                    interior_only, x, ctx->ghost_dev, y,
                                                    b.circ_tab_dev);
     ctx->launches++;
@@ -387,12 +390,13 @@ static int launch_circ(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int int
 }
 
 static int launch_one_bucket(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int interior_only,
-                             const double* x, double* y, cudaStream_t st) {
+                             const double* x, double* y, cudaStream_t st,
+                             const int32_t* cols_dev = nullptr, int count = -1) {
     int rc = RTB200_EUNSUPPORTED;
     if (b.circ_nc > 0) {
 #define X(N_, NC_, P_)                                                                  \
     if (b.n == N_ && b.circ_nc == NC_ && b.circ_p == P_)                                \
-        rc = launch_circ<N_, NC_, P_>(ctx, b, terms, interior_only, x, y, st);
+        rc = launch_circ<N_, NC_, P_>(ctx, b, terms, interior_only, x, y, st, cols_dev, count);
         RT_CIRC_COMBOS(X)
 #undef X
         return rc;
@@ -441,6 +445,32 @@ int rt_launch_apply(rtb200_ctx* ctx, unsigned terms, int interior_only, const do
         cudaStreamWaitEvent(st, ctx->ev_join[s], 0);
     }
     return rc;
+}
+
+// Apply with the face-trace halo exchange of a multi-GPU run.  When the mesh is one
+// circulant bucket (the benchmark case) the columns that read no ghost trace are processed
+// while the exchange (k_pack + grouped ncclSend / ncclRecv) runs on the communication
+// stream; the few columns next to another rank's slab follow once the traces have landed.
+int rt_apply_with_halo(rtb200_ctx* ctx, unsigned terms, int interior_only, const double* x,
+                       double* y, cudaStream_t st) {
+    if (!(terms & RTB200_TERM_BCONV) || ctx->nranks <= 1 || ctx->peer_rank.empty())
+        return rt_launch_apply(ctx, terms, interior_only, x, y, st);
+    int rc;
+    if (!ctx->overlap_ready) {
+        rc = rtb200_halo_exchange(ctx, x, (void*)st);
+        if (rc) return rc;
+        return rt_launch_apply(ctx, terms, interior_only, x, y, st);
+    }
+    const Bucket& b = ctx->buckets[0];
+    RT_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+    RT_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_fork, 0));
+    rc = rtb200_halo_exchange(ctx, x, (void*)ctx->comm_stream);
+    if (rc) return rc;
+    RT_CUDA(ctx, cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
+    rc = launch_one_bucket(ctx, b, terms, interior_only, x, y, st, b.cols_int_dev, b.count_int);
+    cudaStreamWaitEvent(st, ctx->ev_halo, 0);          // always rejoin
+    if (rc) return rc;
+    return launch_one_bucket(ctx, b, terms, interior_only, x, y, st, b.cols_halo_dev, b.count_halo);
 }
 
 int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
@@ -564,6 +594,39 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
         if ((rc = up(a.count, &b.grp_count_dev))) return rc;
         ctx->buckets.push_back(b);
     }
+    // multi-GPU: one circulant bucket -> split its columns into those that read a ghost trace
+    // (face_base <= -2) and the rest, for the overlapped halo exchange of rt_apply_with_halo
+    ctx->overlap_ready = false;
+    if (m->n_peer > 0 && ctx->buckets.size() == 1 && ctx->buckets[0].circ_nc > 0) {
+        Bucket& b = ctx->buckets[0];
+        const auto& cols = acc.begin()->second.cols;
+        std::vector<int32_t> ci, ch;
+        for (int32_t c : cols) {
+            bool ghost = false;
+            for (int f = 0; f < 8; ++f) ghost = ghost || m->face_base[c * 8 + f] <= -2;
+            (ghost ? ch : ci).push_back(c);
+        }
+        auto up1 = [&](const std::vector<int32_t>& h, int32_t** d) -> int {
+            *d = nullptr;
+            if (h.empty()) return RTB200_OK;
+            RT_CUDA(ctx, cudaMalloc((void**)d, sizeof(int32_t) * h.size()));
+            ctx->allocs.push_back(*d);
+            RT_CUDA(ctx, cudaMemcpy(*d, h.data(), sizeof(int32_t) * h.size(), cudaMemcpyHostToDevice));
+            return RTB200_OK;
+        };
+        int rc;
+        if ((rc = up1(ci, &b.cols_int_dev))) return rc;
+        if ((rc = up1(ch, &b.cols_halo_dev))) return rc;
+        b.count_int = (int)ci.size();
+        b.count_halo = (int)ch.size();
+        if (!ctx->comm_stream) {
+            RT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+            RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
+            if (!ctx->ev_fork) RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        }
+        const char* env = getenv("RTB200_HALO_OVERLAP");
+        ctx->overlap_ready = !(env && env[0] == '0');
+    }
     // launch order: most columns x angles first
     ctx->bucket_order.resize(ctx->buckets.size());
     for (size_t i = 0; i < ctx->buckets.size(); ++i) ctx->bucket_order[i] = (int)i;
@@ -601,11 +664,7 @@ extern "C" int rtb200_apply(rtb200_ctx* ctx, unsigned terms, int interior_only,
     if (x_slab_dev == y_slab_dev) return rt_fail(ctx, RTB200_EINVAL, "apply: x and y must not alias");
     if (terms == 0 || (terms & ~RTB200_TERM_ALL)) return rt_fail(ctx, RTB200_EINVAL, "apply: bad term mask");
     cudaStream_t st = (cudaStream_t)stream;
-    if ((terms & RTB200_TERM_BCONV) && ctx->nranks > 1) {
-        rc = rtb200_halo_exchange(ctx, x_slab_dev, stream);
-        if (rc) return rc;
-    }
-    return rt_launch_apply(ctx, terms, interior_only, x_slab_dev, y_slab_dev, st);
+    return rt_apply_with_halo(ctx, terms, interior_only, x_slab_dev, y_slab_dev, st);
 }
 
 extern "C" int rtb200_to_slab(rtb200_ctx* ctx, const double* x_dof_dev, double* x_slab_dev,

@@ -62,6 +62,10 @@ extern "C" void rtb200_destroy(rtb200_ctx* ctx) {
     for (cudaStream_t q : ctx->side_streams) cudaStreamDestroy(q);
     for (cudaEvent_t e : ctx->ev_join) cudaEventDestroy(e);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_halo) cudaEventDestroy(ctx->ev_halo);
+    if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+    ctx->ev_halo = nullptr;
+    ctx->comm_stream = nullptr;
     ctx->side_streams.clear();
     ctx->ev_join.clear();
     ctx->ev_fork = nullptr;

@@ -263,16 +263,12 @@ struct Solver {
     // y = A_ii x (optionally preconditioned from the left): w <- M^-1 A x
     int op(const double* x, double* y, int pc) {
         int rc;
-        if (ctx->nranks > 1) {
-            rc = rtb200_halo_exchange(ctx, x, (void*)st);
-            if (rc) return rc;
-        }
         if (pc) {
-            rc = rt_launch_apply(ctx, RTB200_TERM_ALL, 1, x, wk.t, st);
+            rc = rt_apply_with_halo(ctx, RTB200_TERM_ALL, 1, x, wk.t, st);
             if (rc) return rc;
             return rt_pc_apply(ctx, wk.t, y, st);
         }
-        return rt_launch_apply(ctx, RTB200_TERM_ALL, 1, x, y, st);
+        return rt_apply_with_halo(ctx, RTB200_TERM_ALL, 1, x, y, st);
     }
 };
 
@@ -403,8 +399,7 @@ extern "C" int rtb200_gmres(rtb200_ctx* ctx, const double* b_dev, double* x_dev,
             RT_CUDA(ctx, cudaMemsetAsync(x_dev, 0, sizeof(double) * n, S.st));
             RT_CUDA(ctx, cudaMemcpyAsync(W.V, b_dev, sizeof(double) * n, cudaMemcpyDeviceToDevice, S.st));
         } else {
-            if (ctx->nranks > 1) { rc = rtb200_halo_exchange(ctx, x_dev, stream); if (rc) return rc; }
-            rc = rt_launch_apply(ctx, RTB200_TERM_ALL, 1, x_dev, W.w, S.st);
+            rc = rt_apply_with_halo(ctx, RTB200_TERM_ALL, 1, x_dev, W.w, S.st);
             if (rc) return rc;
             n_apply++;
             k_sub<<<W.nblocks, RED_THREADS, 0, S.st>>>(b_dev, W.w, W.V, S.n2);
@@ -515,8 +510,7 @@ extern "C" int rtb200_gmres(rtb200_ctx* ctx, const double* b_dev, double* x_dev,
     }
 
     // true residual at exit
-    if (ctx->nranks > 1) { rc = rtb200_halo_exchange(ctx, x_dev, stream); if (rc) return rc; }
-    rc = rt_launch_apply(ctx, RTB200_TERM_ALL, 1, x_dev, W.w, S.st);
+    rc = rt_apply_with_halo(ctx, RTB200_TERM_ALL, 1, x_dev, W.w, S.st);
     if (rc) return rc;
     n_apply++;
     k_sub<<<W.nblocks, RED_THREADS, 0, S.st>>>(b_dev, W.w, W.t, S.n2);

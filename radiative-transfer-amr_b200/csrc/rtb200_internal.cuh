@@ -42,6 +42,9 @@ struct Bucket {
     int32_t* grp_count_dev = nullptr;   // [n_groups] columns in the group
     // block-circulant scattering (uniform angular mesh): NC cells of P nodes; 0 = dense
     int circ_nc = 0, circ_p = 0, circ_sig = 0;
+    int32_t* cols_int_dev = nullptr;    // multi-GPU: columns that read no ghost trace ...
+    int32_t* cols_halo_dev = nullptr;   // ... and those that do (rt_apply_with_halo)
+    int count_int = 0, count_halo = 0;
     bool circ_herm = false;             // every block of the spectrum is Hermitian (symmetric Phi)
     bool circ_conforming = false;       // no mortar face in any column of the bucket
     const double* circ_tab_dev = nullptr;
@@ -61,6 +64,9 @@ struct rtb200_ctx {
     std::vector<cudaStream_t> side_streams;     // buckets of an hp mesh run concurrently
     std::vector<cudaEvent_t> ev_join;
     cudaEvent_t ev_fork = nullptr;
+    cudaStream_t comm_stream = nullptr;         // halo exchange overlapped with interior columns
+    cudaEvent_t ev_halo = nullptr;
+    bool overlap_ready = false;
     double* coef_dev = nullptr;
     int64_t n_coef = 0;
     const double* circ_pool_dev = nullptr;
@@ -100,6 +106,8 @@ int rt_cuda(rtb200_ctx* ctx, cudaError_t e, const char* what);
 int rt_launch_apply(rtb200_ctx* ctx, unsigned terms, int interior_only, const double* x,
                     double* y, cudaStream_t st);
 int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m);
+int rt_apply_with_halo(rtb200_ctx* ctx, unsigned terms, int interior_only, const double* x,
+                       double* y, cudaStream_t st);
 // comm.cu
 int rt_allreduce_sum(rtb200_ctx* ctx, double* buf_dev, int count, cudaStream_t st);
 void rt_comm_destroy(rtb200_ctx* ctx);
