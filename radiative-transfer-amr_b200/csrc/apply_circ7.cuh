@@ -73,6 +73,25 @@ struct Circ7Cfg {
     static constexpr int COEF_DOUBLES = 2 * NN;
     static constexpr size_t SMEM = sizeof(double) * (size_t)(2 * U_DOUBLES + W_DOUBLES + T_DOUBLES +
                                                              TAB_DOUBLES + 2 * COEF_DOUBLES);
+    // Real rows of W (the inverse transform's output, read by the streaming phase): each warp
+    // rewrites the region of its own nodes, row stride SWR = P (mod 16) so that the 8-byte
+    // stores of a half-warp ((node, a) at doubles node * SWR + a + const) hit distinct banks
+    // -- the spectrum layout of the same region needs the even stride SW for 16-byte slots.
+    static constexpr int swr() {
+        int v = NT;
+        while ((v & 15) != (P & 15)) ++v;
+        return v <= SW ? v : SW;
+    }
+    static constexpr int SWR = swr();
+    __host__ __device__ static constexpr int node_warp(int n) {      // owner of node n in the FFT phases
+        int w = 0;
+        while (((w + 1) * NN) / WORK_WARPS <= n) ++w;
+        return w;
+    }
+    __host__ __device__ static constexpr int wrow(int n) {           // offset (doubles) of node n's real row
+        const int n0 = (node_warp(n) * NN) / WORK_WARPS;
+        return n0 * SW + (n - n0) * SWR;
+    }
     static constexpr int NA = (NN + 1) / 2;                    // nodes [0, NA) -> half 0, rest -> half 1
     // resident blocks per SM the register allocation aims at: 2 at the benchmark size (320
     // threads, 96 registers), more for the small blocks of low-order / few-cell columns
@@ -340,7 +359,7 @@ __device__ __noinline__ void stream7(
             if (!RT_MINE(i, j)) continue;
             const int n = i * N + j;
             double acc = v[i][j];
-            if (t_sc) acc = fma(-coef_s[NN + n], ws[n * SW], acc);
+            if (t_sc) acc = fma(-coef_s[NN + n], ws[Cfg::wrow(n)], acc);
             bool masked = false;
             if (i == N - 1) masked = masked || m0;
             if (j == N - 1) masked = masked || m1;
@@ -588,7 +607,7 @@ __device__ __noinline__ void fft_i7(double* __restrict__ W, const int warp, cons
     double xs[H];
     split_inverse<NC>(ia, ib, t, xs);
     if (seq_on) {
-        double* dst = W + node * SW + a + t * P;
+        double* dst = W + n0 * SW + dn * Cfg::SWR + a + t * P;      // real-row layout, see Circ7Cfg::wrow
 #pragma unroll
         for (int mm = 0; mm < H; ++mm) dst[2 * mm * P] = xs[mm];
     }

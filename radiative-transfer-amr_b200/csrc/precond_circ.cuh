@@ -177,7 +177,7 @@ k_pc_circ(DevMesh m, const int32_t* __restrict__ cols, int sg, const double shif
     __syncthreads();
     for (int e = tid; e < NN * NTP; e += THREADS) {
         const int node = e / NTP, th = e - node * NTP;
-        y[off + (int64_t)node * NTP + th] = th < NT ? W[node * SW + th] * (1.0 / NC) : 0.0;
+        y[off + (int64_t)node * NTP + th] = th < NT ? W[Cfg::wrow(node) + th] * (1.0 / NC) : 0.0;
     }
 }
 
