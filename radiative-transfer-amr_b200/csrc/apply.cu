@@ -60,10 +60,13 @@ constexpr int AP_WARPS = AP_THREADS / 32;
 constexpr int AP_NTB = 3;     // n-tiles per warp per pass
 constexpr int AP_MAXCG = 8;   // columns per group
 
-// columns per group and m-tiles per chunk for the compile-time sizes
-// (CG*nn <= 64 rows; generic kernels loop over chunks of 8 m-tiles)
-__host__ __device__ constexpr int ap_cg(int nn) { return nn >= 64 ? 1 : (64 / nn > AP_MAXCG ? AP_MAXCG : 64 / nn); }
-__host__ __device__ constexpr int ap_mt(int n) { return n == 0 ? 8 : (ap_cg(n * n) * n * n + 7) / 8; }
+// columns per group (CG*nn <= AP_ROWS rows) and m-tiles per chunk of the scattering GEMM
+// (<= 8 accumulator tiles in registers; larger groups are walked in chunks)
+// Short rows (<= 64 angles: hp meshes with few, low-order angular cells) get groups of up
+// to 128 rows -- fuller blocks, the group's G fragments reused by more rows; long rows
+// keep 64 (one chunk: G is streamed once per group).
+__host__ __device__ constexpr int ap_cg(int nn, int rows = 128) { return nn >= rows ? 1 : (rows / nn > AP_MAXCG ? AP_MAXCG : rows / nn); }
+__host__ __device__ constexpr int ap_mt(int n, int rows) { return n == 0 ? 8 : ((ap_cg(n * n, rows) * n * n + 7) / 8 > 8 ? 8 : (ap_cg(n * n, rows) * n * n + 7) / 8); }
 
 struct GroupTab {
     const int32_t* grp_first;   // [n_groups] first entry in grp_cols
@@ -82,7 +85,7 @@ k_apply(DevMesh m, GroupTab gt, unsigned terms, int interior_only, const double*
         const double* __restrict__ ghost, double* __restrict__ y, int ntps) {
     extern __shared__ __align__(16) double u_s[];
     __shared__ int s_col[AP_MAXCG];
-    constexpr int AP_MT = ap_mt(N);
+    constexpr int AP_MT = ap_mt(N, TH == 128 ? 128 : 64);   // (groups of another size are chunked)
 
     const int g = blockIdx.x;
     const int cg_n = gt.grp_count[g];
@@ -523,7 +526,7 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
         const int nn = k.nx * k.ny;
         const bool circ = ctx->use_circ && m->sig_circ_off && m->sig_circ_off[k.sig] >= 0 && k.n > 0 &&
                           circ_supported(k.n, m->sig_circ_nc[k.sig], m->sig_circ_p[k.sig]);
-        const int cg = circ ? 1 : ap_cg(nn);
+        const int cg = circ ? 1 : ap_cg(nn, m->sig_ntp[k.sig] <= 64 ? 128 : 64);
         auto& v = kv.second;
         if (circ) {
             for (int c : v) {
