@@ -215,3 +215,30 @@ def test_partitioned_apply_equals_single_rank(name, nranks):
     for r, f in enumerate(flats):
         assert np.array_equal(keys[f.col_global], np.array_split(keys, nranks)[r])
     assert sum(f.n_dof for f in flats) == d["x"].size
+
+
+def test_hp_synthetic_mesh_tables_reproduce_the_oracle():
+    """The seeded hp-refined benchmark mesh (configs.hp_synthetic, the small twin of
+    BASELINE configs[4]): the flattened tables, run through the numpy emulation of the
+    kernel, reproduce the oracle's assembled operator term by term; the generator is
+    deterministic."""
+    import emulate as E
+    from oracle import rt_oracle as O
+    from rt_b200 import configs
+    from rt_b200.dg.flatmesh import FlatMesh
+    prob = configs.two_strong_scatterers()
+    mesh = configs.hp_synthetic(level=2)
+    assert configs.hp_synthetic(level=2) == mesh                      # seeded: reproducible
+    ref = O.assemble(mesh, prob.kappa, prob.sigma, prob.Phi)
+    f = FlatMesh(mesh)
+    assert len(f.arrays.sigs) > 1 and f.stats()["exy_tables"] > 0    # really hp: several angular meshes, mortars
+    perm = f.slab_index_of_dof()
+    x = np.random.default_rng(3).standard_normal(f.n_dof)
+    xs = np.zeros(f.n_slab)
+    xs[perm] = x
+    tabs = E.host_tables(f, prob)
+    for terms, key, sign in ((3, "MS", 1.0), (4, "IC", -1.0), (8, "BC", 1.0), (15, "A", 1.0)):
+        y = E.apply_slab(f, *tabs, xs, terms=terms, interior_only=False)[perm]
+        yr = sign * (ref[key] @ x)
+        assert rel_err(y, yr) <= 1e-12, (key, rel_err(y, yr))
+    assert np.array_equal(f.interior_mask_dof(), ref["mask"].astype(bool))
