@@ -465,6 +465,48 @@ def run_b200(args):
                     except Exception as exc:
                         solves[name] = {"error": str(exc)}
                 gm["time_to_solve"] = {"rtol": 1e-8, "max_it": args.solve_max_it, **solves}
+                # ---- a solve carried to convergence and verified, on the 64 x 64-column twin
+                # of the mesh (1.6e7 DoF): same construction of b, rtol 1e-10
+                if na is not None and ns > 6:
+                    op.free_workspace()
+                    flat_s = FlatMesh(MeshArrays.uniform(LS, 6, na, nd), rank=rank, nranks=world)
+                    op_s = RTOperator(flat_s, prob.kappa, prob.sigma, prob.Phi, device=dev)
+                    if world > 1:
+                        op_s.comm_init(rank, world)
+                    g2 = torch.Generator(device=dev); g2.manual_seed(11 + rank)
+                    xs_ = torch.randn(op_s.n_slab, dtype=torch.float64, device=dev, generator=g2)
+                    op_s.mask_slab(xs_, "interior")
+                    bs_ = op_s.apply_slab(xs_, None, 15, True)
+                    sol_s = op_s.zeros_slab()
+
+                    def gnorm(t):
+                        v = torch.linalg.vector_norm(t) ** 2
+                        if world > 1:
+                            dist.all_reduce(v)
+                        return float(v.sqrt())
+
+                    conv = {"mesh": "uniform 64x64 columns x %d cells, ndofs %s" % (2 ** na, nd),
+                            "ndof": int(flat_s.n_dof_global), "rtol": 1e-10}
+                    for name, pcf in (("none", 0), ("node_bjacobi", 1)):
+                        try:
+                            sol_s.zero_()
+                            barrier()
+                            t = time.perf_counter()
+                            info = op_s.gmres(bs_, sol_s, restart=50, max_it=8000 if pcf else 3000,
+                                              rtol=1e-10, atol=0.0,
+                                              orth=2, pc=pcf, x0_nonzero=False)
+                            barrier()
+                            conv[name] = {"seconds": time.perf_counter() - t,
+                                          "iterations": info["iterations"],
+                                          "converged_reason": info["reason"],
+                                          "true_residual_reduction": info["true_res_norm"] / max(gnorm(bs_), 1e-300),
+                                          "rel_error_vs_u_true": gnorm(sol_s - xs_) / max(gnorm(xs_), 1e-300)}
+                        except Exception as exc:
+                            conv[name] = {"error": str(exc)}
+                    gm["time_to_solve_converged"] = conv
+                    op_s.free_workspace()
+                    op_s.close()
+                    del xs_, bs_, sol_s
             op.free_workspace()
             del b, sol
         except Exception as exc:      # report, do not hide
