@@ -86,7 +86,7 @@ __device__ __forceinline__ void solve_real(double (&a)[P][P], double (&b)[P]) {
 }
 
 template <int N, int NC, int P>
-__global__ void __launch_bounds__(Circ7Cfg<N, NC, P>::THREADS, 1)
+__global__ void __launch_bounds__(Circ7Cfg<N, NC, P>::THREADS, Circ7Cfg<N, NC, P>::MINB)
 k_pc_circ(DevMesh m, const int32_t* __restrict__ cols, int sg, const double shift,
           const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ circ_tab) {
     using Cfg = Circ7Cfg<N, NC, P>;
