@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define RTB200_ABI_VERSION 3
+#define RTB200_ABI_VERSION 4
 
 /* error codes */
 #define RTB200_OK            0
@@ -255,6 +255,34 @@ int  rtb200_pc_set_shift(rtb200_ctx* ctx, double shift);
 int  rtb200_nccl_unique_id(char* id128);                 /* 128-byte buffer */
 int  rtb200_comm_init(rtb200_ctx* ctx, const char* id128, int rank, int nranks);
 int  rtb200_halo_exchange(rtb200_ctx* ctx, const double* x_slab_dev, void* stream);
+
+/* ---- AMR error-indicator reductions on the solution the solver leaves on the
+ *      device (replaces the Python loops of
+ *      src/amr/Error_Indicator/error/error_angular_jump.py:14-96 and the two
+ *      integrals behind the hp steering, src/dg/projection/cell_intg_xy.py:14-41
+ *      and col_intg_th.py:14-43).  One launch, one read of the slab.
+ *      Tables (DEVICE pointers, owned by the caller):
+ *        cell_lo / cell_up [n_sigcell]  position inside its signature of the cell
+ *                                       below / above in theta (periodic;
+ *                                       Cell.nhbr_keys, class_Mesh.py:27)
+ *        lag_bot / lag_top [(MAX_NTH+1)][MAX_NTH]  Lagrange basis on the n
+ *                                       Gauss-Legendre nodes at -1 / +1
+ *        lgl_w             [(MAX_NXY+1)][MAX_NXY]  LGL weights (as flatmesh.lgl_w)
+ *        col_cell_off [n_col]  first entry of column c in cell_err2
+ *        col_th_off   [n_col]  first entry of column c in cell_intg_xy
+ *        max_cell_nodes        max over columns of (cells x spatial nodes)
+ *      Outputs (device):
+ *        cell_err2    [sum of cells]    squared cell indicator, cells in sorted-key order
+ *        cell_intg_xy [sum of n_theta]  (dx dy/4) sum_ij w_i w_j u, theta in slab order
+ *        col_intg_th  [n_coef / 2]      sum_theta (dtheta/2) w_a u, node = i*ny + j,
+ *                                       column c at col_coef_off[c] / 2 ------------- */
+int  rtb200_err_angular_jump(rtb200_ctx* ctx, const double* u_slab_dev,
+                             const int32_t* cell_lo_dev, const int32_t* cell_up_dev,
+                             const double* lag_bot_dev, const double* lag_top_dev,
+                             const double* lgl_w_dev, const int64_t* col_cell_off_dev,
+                             const int64_t* col_th_off_dev, int32_t max_cell_nodes,
+                             double* cell_err2_dev, double* cell_intg_xy_dev,
+                             double* col_intg_th_dev, void* stream);
 
 /* ---- instrumentation -------------------------------------------------- */
 int64_t rtb200_launch_count(const rtb200_ctx* ctx);      /* kernels launched so far */

@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_NXY = 12
 MAX_NTH = 16
 
@@ -89,6 +89,8 @@ SYMBOLS = {
     "rtb200_halo_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "rtb200_pc_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rtb200_pc_set_shift": (C.c_int, [C.c_void_p, C.c_double]),
+    "rtb200_err_angular_jump": (C.c_int, [C.c_void_p] + [C.c_void_p] * 8 + [C.c_int32]
+                                + [C.c_void_p] * 4),
     "rtb200_launch_count": (C.c_int64, [C.c_void_p]),
 }
 

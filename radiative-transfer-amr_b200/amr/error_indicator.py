@@ -1,0 +1,397 @@
+"""``Error_Indicator``: where to refine next, and how (h or p).
+
+Drop-in for the reference's ``amr.error_indicator`` package
+(``src/amr/Error_Indicator/class_Error_Indicator.py:12-27``):
+
+    err_ind = Error_Indicator(uh_proj, ref_kind="ang", ref_form="hp", ref_tol=[0.9, 0.0])
+    err_ind.error_angular_jump()
+    mesh = err_ind.ref_by_ind()
+
+Same attributes afterwards (``cols[col_key].error / .do_ref / .ref_form``,
+``cols[col_key].cells[cell_key]...``, ``error``, ``col_max_error``,
+``cell_max_error``, ``error_to_resolve``) and the same JSON on disk
+(``to_file.py:10-60``, ``from_file.py:17-69``).
+
+What differs is where the reductions run: ``error_angular_jump`` makes ONE
+kernel launch on the device-resident solution (``csrc/indicator.cu``) instead of
+the reference's Python loops over every node; when the projection comes from
+``Problem.solve`` the solution is still on the device and nothing is uploaded.
+There is no CPU fallback for it.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+import json
+
+import numpy as np
+from scipy.special import eval_legendre
+
+from .. import consts
+from .. import _lib as L
+from ..dg.projection import Projection, from_file as projection_from_file
+from ..dg.quadrature import quad_xyth, lag_eval
+
+
+class Error_Indicator_Cell:
+    """``error_indicator_cell/class_Error_Indicator_Cell.py:7-11``."""
+
+    def __init__(self, error: float, ref_form: str = "", do_ref: bool = False):
+        self.error = error
+        self.ref_form = ref_form
+        self.do_ref = do_ref
+
+
+class Error_Indicator_Column:
+    """``error_indicator_column/class_Error_Indicator_Column.py:7-13``."""
+
+    def __init__(self, error: float, cells: dict, ref_form: str = "", do_ref: bool = False):
+        self.error = error
+        self.cells = cells
+        self.ref_form = ref_form
+        self.do_ref = do_ref
+
+
+# --------------------------------------------------------------------------- #
+# host tables of the device reductions
+# --------------------------------------------------------------------------- #
+def angular_neighbours(sig):
+    """Position inside the signature of the cell below / above every cell in
+    theta, periodic -- ``Cell.nhbr_keys`` (``class_Mesh.py:27``, ``ref_cell.py:127-165``)
+    for a column of leaves."""
+    n = len(sig.keys)
+    order = np.argsort(np.asarray(sig.th0), kind="stable")
+    rank = np.empty(n, np.int64)
+    rank[order] = np.arange(n)
+    return order[(rank - 1) % n].astype(np.int32), order[(rank + 1) % n].astype(np.int32)
+
+
+def lagrange_end_tables():
+    """l_a(-1), l_a(+1) on the n Gauss-Legendre nodes, n = 1..MAX_NTH
+    (``error_angular_jump.py:39-48``)."""
+    bot = np.zeros((L.MAX_NTH + 1, L.MAX_NTH))
+    top = np.zeros((L.MAX_NTH + 1, L.MAX_NTH))
+    for n in range(1, L.MAX_NTH + 1):
+        thb = quad_xyth(nnodes_th=n)[4]
+        for a in range(n):
+            bot[n, a] = lag_eval(thb, a, -1)
+            top[n, a] = lag_eval(thb, a, 1)
+    return bot, top
+
+
+class IndicatorTables:
+    """Device copies of the tables ``rtb200_err_angular_jump`` reads, for one operator."""
+
+    def __init__(self, op):
+        import torch
+        f = op.flat
+        lo, up = [], []
+        for s in f.arrays.sigs:
+            a, b = angular_neighbours(s)
+            lo.append(a)
+            up.append(b)
+        bot, top = lagrange_end_tables()
+        ncell = f.sig_ncell[f.col_sig].astype(np.int64)
+        nt = f.sig_nt[f.col_sig].astype(np.int64)
+        nn = f.col_nx.astype(np.int64) * f.col_ny
+        self.col_ncell = ncell
+        self.col_nt = nt
+        self.col_cell_off = np.concatenate([[0], np.cumsum(ncell)[:-1]]).astype(np.int64) \
+            if ncell.size else np.zeros(0, np.int64)
+        self.col_th_off = np.concatenate([[0], np.cumsum(nt)[:-1]]).astype(np.int64) \
+            if nt.size else np.zeros(0, np.int64)
+        self.n_cells, self.n_theta = int(ncell.sum()), int(nt.sum())
+        self.n_nodes = int(nn.sum())
+        self.max_cell_nodes = int((ncell * nn).max()) if ncell.size else 1
+
+        def dev(a, dt):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(op.device)
+
+        self.cell_lo = dev(np.concatenate(lo), np.int32)
+        self.cell_up = dev(np.concatenate(up), np.int32)
+        self.lag_bot, self.lag_top = dev(bot, np.float64), dev(top, np.float64)
+        self.lgl_w = dev(f.lgl_w, np.float64)
+        self.col_cell_off_dev = dev(self.col_cell_off if ncell.size else np.zeros(1), np.int64)
+        self.col_th_off_dev = dev(self.col_th_off if nt.size else np.zeros(1), np.int64)
+
+
+def device_angular_jump(op, u_slab):
+    """One launch of ``k_err_angular``.  Returns host arrays
+    ``(cell_err2 [cells], intg_xy [angles], intg_th [nodes])`` in column order."""
+    import torch
+    tab = getattr(op, "_indicator_tables", None)
+    if tab is None:
+        tab = op._indicator_tables = IndicatorTables(op)
+    f64 = dict(dtype=torch.float64, device=op.device)
+    err2 = torch.empty(max(tab.n_cells, 1), **f64)
+    ixy = torch.empty(max(tab.n_theta, 1), **f64)
+    ith = torch.empty(max(tab.n_nodes, 1), **f64)
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    op._call("rtb200_err_angular_jump", op.lib.rtb200_err_angular_jump(
+        op.ctx, p(u_slab), p(tab.cell_lo), p(tab.cell_up), p(tab.lag_bot), p(tab.lag_top),
+        p(tab.lgl_w), p(tab.col_cell_off_dev), p(tab.col_th_off_dev),
+        C.c_int32(tab.max_cell_nodes), p(err2), p(ixy), p(ith), op._stream()))
+    return (err2[:tab.n_cells].cpu().numpy(), ixy[:tab.n_theta].cpu().numpy(),
+            ith[:tab.n_nodes].cpu().numpy(), tab)
+
+
+# --------------------------------------------------------------------------- #
+class Error_Indicator:
+    def __init__(self, proj: Projection, ref_kind: str = "all", ref_form: str = "hp",
+                 ref_tol: list = [consts.INF, consts.INF]):
+        self.proj = proj
+        self.ref_kind = ref_kind
+        self.ref_form = ref_form
+        [self.ang_ref_tol, self.spt_ref_tol] = ref_tol
+        self._intg_xy = None      # {(col_key, cell_key): [nth]} from the device reduction
+        self._intg_th = None      # {col_key: [nx, ny]}
+
+    # ---- device state ---------------------------------------------------- #
+    def _device_solution(self):
+        """(operator, slab-order device vector) of ``self.proj``: the pair
+        ``Problem.solve`` left on the projection, else a table-only operator for
+        the projection's mesh and an upload of its values."""
+        dev = getattr(self.proj, "_device", None)
+        if dev is not None:
+            op, u_slab = dev
+            if getattr(op, "ctx", None) is not None and op.ctx.value and \
+                    op.flat.nranks == 1 and op.n == self.proj.mesh.get_ndof():
+                return op, u_slab
+        from ..rt.operator import RTOperator
+        zero = lambda x, y: np.zeros(np.broadcast(x, y).shape)          # noqa: E731
+        iso = lambda th0, th1: 1. / (2. * consts.PI) + 0. * (th0 - th1)  # noqa: E731
+        op = RTOperator(self.proj.mesh, zero, zero, iso)
+        u_slab = op.to_slab(self.proj.to_vector())
+        self.proj._device = (op, u_slab)
+        return op, u_slab
+
+    # ---- indicators -------------------------------------------------------- #
+    def error_angular_jump(self) -> None:
+        """Mean squared jump of the solution across the angular faces of every
+        cell (``error/error_angular_jump.py:14-138``)."""
+        op, u_slab = self._device_solution()
+        err2, ixy, ith, tab = device_angular_jump(op, u_slab)
+
+        cols: dict = {}
+        col_max_err = -consts.INF
+        cell_max_err = -consts.INF
+        mesh_err = 0.
+        self._intg_xy, self._intg_th = {}, {}
+        cell_err = np.sqrt(err2)
+        for c, (col_key, col) in enumerate(sorted(self.proj.cols.items())):
+            assert col.is_lf
+            c0, t0 = int(tab.col_cell_off[c]), int(tab.col_th_off[c])
+            nx, ny = col.ndofs
+            self._intg_th[col_key] = (int(op.flat.col_coef_off[c]) // 2, nx, ny)
+            cells: dict = {}
+            col_err = 0.
+            for k, (cell_key, cell) in enumerate(sorted(col.cells.items())):
+                assert cell.is_lf
+                e2 = float(err2[c0 + k])
+                col_err += e2
+                mesh_err += e2
+                cells[cell_key] = Error_Indicator_Cell(float(cell_err[c0 + k]))
+                cell_max_err = max(cell_max_err, float(cell_err[c0 + k]))
+                nth = cell.ndofs[0]
+                self._intg_xy[(col_key, cell_key)] = (t0, nth)
+                t0 += nth
+            cols[col_key] = Error_Indicator_Column(float(np.sqrt(col_err)), cells)
+            col_max_err = max(col_max_err, float(np.sqrt(col_err)))
+        self._ixy, self._ith = ixy, ith
+
+        self.cols = cols
+        self.col_max_error = col_max_err
+        self.cell_max_error = cell_max_err
+        self.error = float(np.sqrt(mesh_err))
+        self._mark()
+
+    def error_random(self, rng=None) -> None:
+        """Uniform random indicator per cell (``error/error_random.py:15-91``)."""
+        if rng is None:
+            rng = np.random.default_rng()
+        cols: dict = {}
+        col_max_err = -consts.INF
+        cell_max_err = -consts.INF
+        mesh_err = 0.
+        for col_key, col in sorted(self.proj.mesh.cols.items()):
+            assert col.is_lf
+            col_err = 0.
+            cells: dict = {}
+            for cell_key, cell in sorted(col.cells.items()):
+                assert cell.is_lf
+                cell_err = rng.random()
+                col_err += cell_err
+                mesh_err += cell_err
+                cells[cell_key] = Error_Indicator_Cell(cell_err)
+                cell_max_err = max(cell_max_err, cell_err)
+            cols[col_key] = Error_Indicator_Column(col_err, cells)
+            col_max_err = max(col_max_err, col_err)
+        self.cols = cols
+        self.col_max_error = col_max_err
+        self.cell_max_error = cell_max_err
+        self.error = mesh_err
+        self._mark()
+
+    def _mark(self) -> None:
+        """Refinement flags and hp steering from the stored errors (the common
+        tail of every indicator, e.g. ``error_angular_jump.py:104-138``)."""
+        self.error_to_resolve = 0.
+        ang_ref_thrsh = self.ang_ref_tol * self.cell_max_error
+        spt_ref_thrsh = self.spt_ref_tol * self.col_max_error
+        for col_key, col in sorted(self.proj.cols.items()):
+            assert col.is_lf
+            ecol = self.cols[col_key]
+            if self.ref_kind in ["spt", "all"]:
+                if ecol.error >= spt_ref_thrsh:
+                    ecol.do_ref = True
+                    self.error_to_resolve += ecol.error
+                    ecol.ref_form = self.col_hp_steer(col_key) if self.ref_form == "hp" \
+                        else self.ref_form
+                else:
+                    ecol.do_ref = False
+            if self.ref_kind in ["ang", "all"]:
+                for cell_key, cell in sorted(col.cells.items()):
+                    assert cell.is_lf
+                    ecell = ecol.cells[cell_key]
+                    if ecell.error >= ang_ref_thrsh:
+                        ecell.do_ref = True
+                        self.error_to_resolve += ecell.error
+                        ecell.ref_form = self.cell_hp_steer(col_key, cell_key) \
+                            if self.ref_form == "hp" else self.ref_form
+                    else:
+                        ecell.do_ref = False
+
+    # ---- hp steering -------------------------------------------------------- #
+    def _cell_intg_xy(self, col_key, cell_key) -> np.ndarray:
+        if self._intg_xy is not None and (col_key, cell_key) in self._intg_xy:
+            t0, nth = self._intg_xy[(col_key, cell_key)]
+            return self._ixy[t0:t0 + nth]
+        return self.proj.cell_intg_xy(col_key, cell_key)
+
+    def _col_intg_th(self, col_key) -> np.ndarray:
+        if self._intg_th is not None and col_key in self._intg_th:
+            n0, nx, ny = self._intg_th[col_key]
+            return self._ith[n0:n0 + nx * ny].reshape(nx, ny)
+        return self.proj.col_intg_th(col_key)
+
+    def cell_hp_steer(self, col_key: int, cell_key: int) -> str:
+        """'p' when the highest angular Legendre coefficient of the spatially
+        integrated solution decays fast enough, else 'h' (``cell_hp_steer.py:16-48``)."""
+        cell = self.proj.cols[col_key].cells[cell_key]
+        assert cell.is_lf
+        [nth] = cell.ndofs[:]
+        _, _, _, _, thb, wth = quad_xyth(nnodes_th=nth)
+        thb = np.asarray(thb).reshape([1, nth])
+        wth = np.asarray(wth).reshape([1, nth])
+        uh_hat = np.asarray(self._cell_intg_xy(col_key, cell_key)).reshape([1, nth])
+        L_nthr = eval_legendre(nth - 1, thb)
+        a_nth = (2. * nth - 1.) / 2. * (wth * uh_hat) @ L_nthr.transpose()
+        ath_nth_sq = (a_nth[0, 0]) ** 2 * (2. / (2. * nth - 1.))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            lp = np.log((2. * nth - 1.) / (2 * ath_nth_sq)) / (2. * np.log(nth - 1))
+        return "p" if lp - 0.5 >= float(nth) else "h"
+
+    def col_hp_steer(self, col_key: int) -> str:
+        """Spatial counterpart on the angle-integrated solution (``col_hp_steer.py:15-64``)."""
+        col = self.proj.cols[col_key]
+        assert col.is_lf
+        [nx, ny] = col.ndofs[:]
+        xxb, wx, yyb, wy, _, _ = quad_xyth(nnodes_x=nx, nnodes_y=ny)
+        xxb = np.asarray(xxb).reshape([1, nx])
+        wx = np.asarray(wx).reshape([nx, 1])
+        yyb = np.asarray(yyb).reshape([1, ny])
+        wy = np.asarray(wy).reshape([1, ny])
+        w_uh = wx * wy * np.asarray(self._col_intg_th(col_key))
+
+        L_nxm = eval_legendre(nx - 1, xxb)
+        ndofs_y = np.arange(0, ny).reshape([1, ny])
+        L_jn = eval_legendre(ndofs_y.transpose(), yyb)
+        a_nxj = (2. * nx - 1.) * (2. * ndofs_y + 1.) / 4. * (L_nxm @ w_uh @ L_jn.transpose())
+        ax_nx_sq = 0
+        for jj in range(0, ny):
+            ax_nx_sq += (a_nxj[0, jj]) ** 2 * (2. / (2. * jj + 1.))
+
+        ndofs_x = np.arange(0, nx).reshape([nx, 1])
+        L_im = eval_legendre(ndofs_x, xxb)
+        L_nyn = eval_legendre(ny - 1, yyb)
+        a_iny = (2. * ndofs_x + 1.) * (2. * ny - 1.) / 4. * (L_im @ w_uh @ L_nyn.transpose())
+        ay_ny_sq = 0
+        for ii in range(0, nx):
+            ay_ny_sq += (a_iny[ii, 0]) ** 2 * (2. / (2. * ii + 1.))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            term_0 = np.log((2. * nx - 1.) / (2 * ax_nx_sq)) / (2. * np.log(nx - 1.))
+            term_1 = np.log((2. * ny - 1.) / (2 * ay_ny_sq)) / (2. * np.log(ny - 1.))
+        lp = 0.5 * (term_0 + term_1)
+        return "p" if lp - 0.5 >= 0.5 * (nx + ny) else "h"
+
+    # ---- refinement ---------------------------------------------------------- #
+    def ref_by_ind(self):
+        """Refined copy of the projection's mesh (``ref_by_ind.py:14-46``)."""
+        mesh = copy.deepcopy(self.proj.mesh)
+        for col_key, col in sorted(self.proj.mesh.cols.items()):
+            assert col.is_lf
+            if col_key not in mesh.cols.keys():      # already split to keep the mesh 1-irregular
+                continue
+            if self.ref_kind in ["ang", "all"]:
+                for cell_key, cell in sorted(col.cells.items()):
+                    assert cell.is_lf
+                    if cell_key in mesh.cols[col_key].cells.keys():
+                        ecell = self.cols[col_key].cells[cell_key]
+                        if ecell.do_ref:
+                            mesh.ref_cell(col_key, cell_key, form=ecell.ref_form)
+            if self.ref_kind in ["spt", "all"]:
+                ecol = self.cols[col_key]
+                if ecol.do_ref:
+                    mesh.ref_col(col_key, kind="spt", form=ecol.ref_form)
+        return mesh
+
+    # ---- files ------------------------------------------------------------------ #
+    def to_file(self, file_path: str = "err_ind.json", **kwargs) -> None:
+        """Same JSON as ``to_file.py:10-60``."""
+        opts = {"write_mesh": True, "mesh_file_path": "mesh.json", "write_projection": True,
+                "projection_file_path": "projection.npy", **kwargs}
+        if opts["write_projection"]:
+            self.proj.to_file(opts["projection_file_path"], **opts)
+        d = {"ref_kind": self.ref_kind, "ref_form": self.ref_form,
+             "ang_ref_tol": self.ang_ref_tol, "spt_ref_tol": self.spt_ref_tol,
+             "error": self.error, "error_to_resolve": self.error_to_resolve,
+             "col_max_error": self.col_max_error, "cell_max_error": self.cell_max_error}
+        cols = {}
+        for col_key, col in sorted(self.proj.mesh.cols.items()):
+            assert col.is_lf
+            ecol = self.cols[col_key]
+            cells = {}
+            for cell_key, cell in sorted(col.cells.items()):
+                assert cell.is_lf
+                ecell = ecol.cells[cell_key]
+                cells[cell_key] = {"do_ref": ecell.do_ref, "ref_form": ecell.ref_form,
+                                   "error": ecell.error}
+            cols[col_key] = {"do_ref": ecol.do_ref, "ref_form": ecol.ref_form,
+                             "error": ecol.error, "cells": cells}
+        d["cols"] = cols
+        with open(file_path, "w") as out_file:
+            json.dump(d, out_file)
+
+
+def from_file(mesh_file_path: str = "mesh.json", projection_file_path: str = "projection.npy",
+              err_ind_file_path: str = "err_ind.json") -> Error_Indicator:
+    """Read what ``Error_Indicator.to_file`` wrote (``from_file.py:17-69``)."""
+    proj = projection_from_file(mesh_file_path, projection_file_path)
+    with open(err_ind_file_path, "r") as in_file:
+        d = json.load(in_file)
+    err_ind = Error_Indicator(proj=proj, ref_kind=d["ref_kind"], ref_form=d["ref_form"],
+                              ref_tol=[d["ang_ref_tol"], d["spt_ref_tol"]])
+    err_ind.error = d["error"]
+    err_ind.error_to_resolve = d["error_to_resolve"]
+    err_ind.col_max_error = d["col_max_error"]
+    err_ind.cell_max_error = d["cell_max_error"]
+    cols = {}
+    for col_key in sorted(d["cols"].keys()):
+        cd = d["cols"][col_key]
+        cells = {}
+        for cell_key in sorted(cd["cells"].keys()):
+            ce = cd["cells"][cell_key]
+            cells[int(cell_key)] = Error_Indicator_Cell(ce["error"], ce["ref_form"], ce["do_ref"])
+        cols[int(col_key)] = Error_Indicator_Column(cd["error"], cells, cd["ref_form"], cd["do_ref"])
+    err_ind.cols = cols
+    return err_ind

@@ -1,0 +1,138 @@
+// AMR error-indicator reductions on the device-resident solution (sm_100a).
+//
+// After a solve the reference pulls the solution into a Projection and walks it
+// with Python loops to decide where to refine:
+//
+//   error_angular_jump   (src/amr/Error_Indicator/error/error_angular_jump.py:14-138)
+//       top / bottom trace of every angular cell (Lagrange basis at +1 / -1 of the
+//       pulled-back cell), squared jumps against the lower / upper neighbour cell,
+//       integrated over the column's LGL nodes:
+//           err2[c][K] = 1/4 sum_ij w_i w_j 1/2 ((bot_K - top_lo)^2 + (top_K - bot_up)^2)
+//   cell_intg_xy         (src/dg/projection/cell_intg_xy.py:14-41)   input of cell_hp_steer
+//           I_xy[c][theta] = (dx dy / 4) sum_ij w_i w_j u[i][j][theta]
+//   col_intg_th          (src/dg/projection/col_intg_th.py:14-43)    input of col_hp_steer
+//           I_th[c][node]  = sum_theta (dtheta/2) w_a u[node][theta]
+//
+// k_err_angular does the three reductions in one launch on the slab-order vector
+// the solver leaves on the device (one block per column; the slab is read from
+// HBM once, 8 B/DoF, the re-reads of phases 2-3 hit L1/L2).  What is left for the
+// host are the thresholds and the Legendre-coefficient test of the flagged cells
+// (rt_b200.amr.Error_Indicator).
+#include "rtb200_internal.cuh"
+
+namespace {
+
+constexpr int EI_THREADS = 128;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(EI_THREADS)
+k_err_angular(DevMesh m, const double* __restrict__ u, const int32_t* __restrict__ cell_lo,
+              const int32_t* __restrict__ cell_up, const double* __restrict__ lag_bot,
+              const double* __restrict__ lag_top, const double* __restrict__ lgl_w,
+              const int64_t* __restrict__ col_cell_off, const int64_t* __restrict__ col_th_off,
+              double* __restrict__ cell_err2, double* __restrict__ intg_xy,
+              double* __restrict__ intg_th) {
+    extern __shared__ __align__(16) double ei_s[];
+    const int c = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = EI_THREADS / 32;
+    const int nx = m.col_nx[c], ny = m.col_ny[c], nn = nx * ny;
+    const int sg = m.col_sig[c];
+    const int nt = m.sig_nt[sg], ntp = m.sig_ntp[sg];
+    const int64_t tp0 = m.sig_th0[sg];
+    const int cell0 = m.sig_cell0[sg], ncell = m.sig_ncell[sg];
+    const double* __restrict__ uc = u + m.col_slab_off[c];
+    const double* __restrict__ wx = lgl_w + nx * RT_MAXN;
+    const double* __restrict__ wy = lgl_w + ny * RT_MAXN;
+    double* const tops = ei_s;                       // [ncell][nn]
+    double* const bots = ei_s + (size_t)ncell * nn;  // [ncell][nn]
+
+    // ---- traces at the upper / lower end of every cell (error_angular_jump.py:31-51) ---- //
+    for (int e = tid; e < ncell * nn; e += EI_THREADS) {
+        const int K = e / nn, n = e - K * nn;
+        const int nth = m.cell_nth[cell0 + K], tho = m.cell_thoff[cell0 + K];
+        const double* __restrict__ lb = lag_bot + nth * RTB200_MAX_NTH;
+        const double* __restrict__ lt = lag_top + nth * RTB200_MAX_NTH;
+        const double* __restrict__ row = uc + (int64_t)n * ntp + tho;
+        double t = 0.0, b = 0.0;
+        for (int a = 0; a < nth; ++a) {
+            const double v = row[a];
+            t = fma(v, lt[a], t);
+            b = fma(v, lb[a], b);
+        }
+        tops[e] = t;
+        bots[e] = b;
+    }
+    __syncthreads();
+
+    // ---- squared jumps, integrated over the spatial nodes (:56-96): warp per cell -------- //
+    for (int K = warp; K < ncell; K += NW) {
+        const int lo = cell_lo[cell0 + K], up = cell_up[cell0 + K];
+        double s = 0.0;
+        for (int n = lane; n < nn; n += 32) {
+            const int i = n / ny, j = n - i * ny;
+            const double dl = bots[K * nn + n] - tops[lo * nn + n];
+            const double du = tops[K * nn + n] - bots[up * nn + n];
+            s = fma(wx[i] * wy[j], 0.5 * (dl * dl + du * du), s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) cell_err2[col_cell_off[c] + K] = 0.25 * s;
+    }
+
+    // ---- spatial integral per angle (cell_intg_xy.py:24-39): thread per theta ------------ //
+    const double dcoef = 0.25 * m.col_dx[c] * m.col_dy[c];
+    for (int th = tid; th < nt; th += EI_THREADS) {
+        double s = 0.0;
+        for (int n = 0; n < nn; ++n) {
+            const int i = n / ny, j = n - i * ny;
+            s = fma(wx[i] * wy[j], uc[(int64_t)n * ntp + th], s);
+        }
+        intg_xy[col_th_off[c] + th] = dcoef * s;
+    }
+
+    // ---- angular integral per node (col_intg_th.py:22-41): warp per node ----------------- //
+    const int64_t n0 = m.col_coef_off[c] >> 1;
+    for (int n = warp; n < nn; n += NW) {
+        const double* __restrict__ row = uc + (int64_t)n * ntp;
+        double s = 0.0;
+        for (int th = lane; th < nt; th += 32) s = fma(m.th_wt[tp0 + th], row[th], s);
+        s = warp_sum(s);
+        if (lane == 0) intg_th[n0 + n] = s;
+    }
+}
+
+}  // namespace
+
+extern "C" int rtb200_err_angular_jump(rtb200_ctx* ctx, const double* u_slab_dev,
+                                       const int32_t* cell_lo_dev, const int32_t* cell_up_dev,
+                                       const double* lag_bot_dev, const double* lag_top_dev,
+                                       const double* lgl_w_dev, const int64_t* col_cell_off_dev,
+                                       const int64_t* col_th_off_dev, int32_t max_cell_nodes,
+                                       double* cell_err2_dev, double* cell_intg_xy_dev,
+                                       double* col_intg_th_dev, void* stream) {
+    if (!ctx) return RTB200_EINVAL;
+    if (!ctx->have_mesh) return rt_fail(ctx, RTB200_ESTATE, "rtb200_err_angular_jump: no mesh set");
+    if (!u_slab_dev || !cell_lo_dev || !cell_up_dev || !lag_bot_dev || !lag_top_dev || !lgl_w_dev ||
+        !col_cell_off_dev || !col_th_off_dev || !cell_err2_dev || !cell_intg_xy_dev || !col_intg_th_dev)
+        return rt_fail(ctx, RTB200_EINVAL, "rtb200_err_angular_jump: null pointer");
+    if (max_cell_nodes <= 0) return rt_fail(ctx, RTB200_EINVAL, "rtb200_err_angular_jump: max_cell_nodes <= 0");
+    const size_t smem = 2 * sizeof(double) * (size_t)max_cell_nodes;
+    if (smem > 200 * 1024)
+        return rt_fail(ctx, RTB200_EUNSUPPORTED,
+                       "rtb200_err_angular_jump: a column with more than 12800 (cell, node) pairs");
+    if (ctx->dm.n_col == 0) return RTB200_OK;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (smem > 48 * 1024)
+        RT_CUDA(ctx, cudaFuncSetAttribute(k_err_angular, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_err_angular<<<ctx->dm.n_col, EI_THREADS, smem, (cudaStream_t)stream>>>(
+        ctx->dm, u_slab_dev, cell_lo_dev, cell_up_dev, lag_bot_dev, lag_top_dev, lgl_w_dev,
+        col_cell_off_dev, col_th_off_dev, cell_err2_dev, cell_intg_xy_dev, col_intg_th_dev);
+    ctx->launches++;
+    RT_CUDA(ctx, cudaGetLastError());
+    return RTB200_OK;
+}

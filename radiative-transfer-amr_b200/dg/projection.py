@@ -2,7 +2,8 @@
 
 Drop-in for the reference's ``dg.projection`` (``class_Projection.py:17-98``,
 ``to_vector.py:11-44``, ``from_vector.py:11-40``, ``to_file.py:10-19``,
-``from_file.py:14-21``, ``push_pull.py:10-26``).  A ``Projection`` stores one
+``from_file.py:14-21``, ``push_pull.py:10-26``, ``cell_intg_xy.py:14-41``,
+``col_intg_th.py:14-43``, ``intg_th.py:12-32``).  A ``Projection`` stores one
 ``vals[nx, ny, nth]`` array per cell; ``to_vector``/``from_vector`` fix the
 global vector layout used at the solver boundary.
 """
@@ -12,7 +13,7 @@ import copy
 
 import numpy as np
 
-from .mesh import Mesh, from_file as mesh_from_file
+from .mesh import Mesh, from_file as mesh_from_file, remove_th
 from .quadrature import quad_xyth
 
 
@@ -137,6 +138,33 @@ class Projection:
                 g += n
         return self
 
+    def cell_intg_xy(self, col_key: int, cell_key: int) -> np.ndarray:
+        """Spatial integral of one cell per angular node, ``[nth]``
+        (``cell_intg_xy.py:14-41``)."""
+        col = self.cols[col_key]
+        assert col.is_lf
+        x0, y0, x1, y1 = col.pos
+        nx, ny = col.ndofs
+        _, wx, _, wy, _, _ = quad_xyth(nnodes_x=nx, nnodes_y=ny)
+        w = np.asarray(wx).reshape(nx, 1, 1) * np.asarray(wy).reshape(1, ny, 1)
+        cell = col.cells[cell_key]
+        assert cell.is_lf
+        return ((x1 - x0) * (y1 - y0) / 4.) * np.sum(w * cell.vals, axis=(0, 1))
+
+    def col_intg_th(self, col_key: int) -> np.ndarray:
+        """Angular integral of one column per spatial node, ``[nx, ny]``
+        (``col_intg_th.py:14-43``)."""
+        col = self.cols[col_key]
+        assert col.is_lf
+        nx, ny = col.ndofs
+        out = np.zeros([nx, ny])
+        for _, cell in sorted(col.cells.items()):
+            assert cell.is_lf
+            th0, th1 = cell.pos
+            _, _, _, _, _, wth = quad_xyth(nnodes_th=cell.ndofs[0])
+            out += ((th1 - th0) / 2.) * np.sum(np.asarray(wth).reshape(1, 1, -1) * cell.vals, axis=2)
+        return out
+
     def to_file(self, file_path: str = "projection.npy", **kwargs) -> None:
         """Raw float64 dump of the global vector (+ mesh JSON), byte-compatible
         with ``dg/projection/to_file.py:10-19``."""
@@ -147,6 +175,18 @@ class Projection:
 
     def __eq__(self, other):
         return self.mesh == other.mesh and self.cols == other.cols
+
+
+def intg_th(projection: Projection) -> Projection:
+    """Angle-integrated field as a projection on the mesh without its angular
+    dimension (``intg_th.py:12-32``)."""
+    out = Projection(remove_th(projection.mesh))
+    for col_key, col in sorted(projection.cols.items()):
+        assert col.is_lf
+        nx, ny = col.ndofs
+        cell_key = list(out.cols[col_key].cells.keys())[0]
+        out.cols[col_key].cells[cell_key].vals = projection.col_intg_th(col_key).reshape(nx, ny, 1)
+    return out
 
 
 def from_file(mesh_file_path: str = "mesh.json",

@@ -236,8 +236,12 @@ class Problem:
         torch.cuda.synchronize(op.device)
         t_solve = perf_counter() - t1
 
-        uh_vec = op.from_slab(x + g_b).cpu().numpy()      # merge_vectors.py:14-56
+        u_slab = x + g_b                                  # merge_vectors.py:14-56
+        uh_vec = op.from_slab(u_slab).cpu().numpy()
         uh_proj = Projection(mesh).from_vector(uh_vec)
+        # the solution stays on the device for the error indicators of the AMR loop
+        # (rt_b200.amr.Error_Indicator reads it in place)
+        uh_proj._device = (op, u_slab)
 
         hist = info["history"]
         convergence_info = {"converged_reason": info["reason"],

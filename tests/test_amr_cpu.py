@@ -1,0 +1,176 @@
+"""CPU tests of the AMR layer: the oracle against the reference's golden outputs,
+host tables of the device reductions, hp steering, refinement by indicator, files."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_cases, load_golden
+
+import rt_b200  # noqa: F401
+from rt_b200 import consts
+from rt_b200.amr import Error_Indicator, Error_Indicator_Cell, Error_Indicator_Column, from_file
+from rt_b200.amr.error_indicator import angular_neighbours, lagrange_end_tables
+from rt_b200.dg.flatmesh import FlatMesh, MeshArrays
+from rt_b200.dg.mesh import from_file as mesh_from_file
+from rt_b200.dg.projection import Projection, intg_th
+from oracle import amr_oracle as AO
+
+FORM = {0: "", 1: "h", 2: "p"}
+
+
+def amr_golden(case):
+    return dict(np.load(os.path.join(GOLDEN, case + ".amr.npz")))
+
+
+def close(a, b, rtol=1e-11):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    scale = max(np.max(np.abs(b)), 1e-300)
+    return np.max(np.abs(a - b)) <= rtol * scale
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_oracle_matches_reference(case):
+    mesh, data, _ = load_golden(case)
+    g = amr_golden(case)
+    e2 = AO.angular_jump(mesh, data["u"])
+    assert close(np.sqrt(e2), g["aj_cell_err"])
+    ncell = [len(col.cells) for _, col in sorted(mesh.cols.items())]
+    col = np.sqrt(np.add.reduceat(e2, np.concatenate([[0], np.cumsum(ncell)[:-1]])))
+    assert close(col, g["aj_col_err"])
+    assert close(np.sqrt(e2.sum()), g["aj_scalars"][0])
+    assert close(AO.cell_intg_xy(mesh, data["u"]), g["intg_xy"])
+    assert close(AO.col_intg_th(mesh, data["u"]), g["intg_th"])
+    s2 = AO.spatial_jump(mesh, data["u"])
+    assert close(np.sqrt(s2), g["sj_col_err"], 1e-10)
+    assert close(np.sqrt(s2.sum()), g["sj_scalars"][0], 1e-10)
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_projection_integrals(case):
+    mesh, data, _ = load_golden(case)
+    g = amr_golden(case)
+    proj = Projection(mesh).from_vector(data["u"])
+    ixy = np.concatenate([proj.cell_intg_xy(ck, kk) for ck, col in sorted(mesh.cols.items())
+                          for kk in sorted(col.cells)])
+    ith = np.concatenate([proj.col_intg_th(ck).reshape(-1) for ck in sorted(mesh.cols)])
+    assert close(ixy, g["intg_xy"]) and close(ith, g["intg_th"])
+    flat = intg_th(proj)
+    assert not flat.mesh.has_th
+    ck = sorted(mesh.cols)[0]
+    assert np.array_equal(flat.cols[ck].cells[0].vals[:, :, 0], proj.col_intg_th(ck))
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_angular_neighbour_table(case):
+    """cell_lo / cell_up of the device kernel = Cell.nhbr_keys of every column."""
+    mesh, _, _ = load_golden(case)
+    A = MeshArrays.from_mesh(mesh)
+    for c, ck in enumerate(sorted(mesh.cols)):
+        sig = A.sigs[A.sig[c]]
+        lo, up = angular_neighbours(sig)
+        keys = [int(k) for k in sig.keys]
+        for k, kk in enumerate(keys):
+            nb = mesh.cols[ck].cells[kk].nhbr_keys
+            assert [keys[lo[k]], keys[up[k]]] == list(nb)
+
+
+def test_lagrange_end_tables():
+    bot, top = lagrange_end_tables()
+    for n in range(1, 17):
+        assert abs(bot[n, :n].sum() - 1) < 1e-12 and abs(top[n, :n].sum() - 1) < 1e-12
+        assert np.allclose(bot[n, :n], top[n, :n][::-1], rtol=0, atol=1e-12)
+        assert np.all(bot[n, n:] == 0)
+
+
+def _indicator_from_golden(case, kind):
+    """An Error_Indicator whose errors are the reference's (no device needed): exercises
+    thresholds, hp steering, ref_by_ind and the file formats on the host."""
+    mesh, data, _ = load_golden(case)
+    g = amr_golden(case)
+    proj = Projection(mesh).from_vector(data["u"])
+    ei = Error_Indicator(proj, ref_kind="all" if kind == "aj" else "spt", ref_form="hp",
+                         ref_tol=list(g["ref_tol"]))
+    cols, k = {}, 0
+    for c, (ck, col) in enumerate(sorted(mesh.cols.items())):
+        cells = {}
+        for kk in sorted(col.cells):
+            cells[kk] = Error_Indicator_Cell(float(g["aj_cell_err"][k]) if kind == "aj"
+                                             else -consts.INF)
+            k += 1
+        cols[ck] = Error_Indicator_Column(float(g[kind + "_col_err"][c]), cells)
+    ei.cols = cols
+    ei.error, _, ei.col_max_error, ei.cell_max_error = [float(v) for v in g[kind + "_scalars"]]
+    ei._mark()
+    return ei, mesh, g
+
+
+@pytest.mark.parametrize("case", golden_cases())
+@pytest.mark.parametrize("kind", ["aj", "sj"])
+def test_flags_and_hp_steering_match_reference(case, kind):
+    ei, mesh, g = _indicator_from_golden(case, kind)
+    col_ref = np.array([ei.cols[ck].do_ref for ck in sorted(mesh.cols)])
+    col_form = [ei.cols[ck].ref_form for ck in sorted(mesh.cols)]
+    assert np.array_equal(col_ref, g[kind + "_col_ref"])
+    assert col_form == [FORM[int(v)] for v in g[kind + "_col_form"]]
+    assert close(ei.error_to_resolve, g[kind + "_scalars"][1])
+    if kind == "aj":
+        cell_ref = np.array([ei.cols[ck].cells[kk].do_ref for ck, col in sorted(mesh.cols.items())
+                             for kk in sorted(col.cells)])
+        cell_form = [ei.cols[ck].cells[kk].ref_form for ck, col in sorted(mesh.cols.items())
+                     for kk in sorted(col.cells)]
+        assert np.array_equal(cell_ref, g["aj_cell_ref"])
+        assert cell_form == [FORM[int(v)] for v in g["aj_cell_form"]]
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_ref_by_ind_matches_reference(case):
+    ei, mesh, _ = _indicator_from_golden(case, "aj")
+    refined = ei.ref_by_ind()
+    want = mesh_from_file(os.path.join(GOLDEN, case + ".amr_refined.mesh.json"))
+    assert refined == want
+    assert ei.proj.mesh == mesh            # the indicator's own mesh is untouched
+
+
+def test_error_indicator_files_round_trip(tmp_path):
+    ei, mesh, _ = _indicator_from_golden("hp_mixed", "aj")
+    paths = dict(mesh_file_path=str(tmp_path / "mesh.json"),
+                 projection_file_path=str(tmp_path / "uh.npy"))
+    ei.to_file(str(tmp_path / "err_ind.json"), **paths)
+    with open(tmp_path / "err_ind.json") as fh:
+        d = json.load(fh)
+    assert set(d) == {"ref_kind", "ref_form", "ang_ref_tol", "spt_ref_tol", "error",
+                      "error_to_resolve", "col_max_error", "cell_max_error", "cols"}
+    back = from_file(paths["mesh_file_path"], paths["projection_file_path"],
+                     str(tmp_path / "err_ind.json"))
+    assert back.proj == ei.proj and back.error == ei.error
+    for ck, col in sorted(mesh.cols.items()):
+        assert back.cols[ck].do_ref == ei.cols[ck].do_ref
+        assert back.cols[ck].ref_form == ei.cols[ck].ref_form
+        for kk in col.cells:
+            assert back.cols[ck].cells[kk].error == ei.cols[ck].cells[kk].error
+
+
+def test_error_random_is_seeded_like_the_reference():
+    mesh, data, _ = load_golden("c1_uniform")
+    proj = Projection(mesh).from_vector(data["u"])
+    ei = Error_Indicator(proj, ref_kind="ang", ref_form="h", ref_tol=[0.5, 0.5])
+    ei.error_random(np.random.default_rng(3))
+    rng = np.random.default_rng(3)
+    want = [rng.random() for _ in range(64)]
+    got = [ei.cols[ck].cells[kk].error for ck, col in sorted(mesh.cols.items())
+           for kk in sorted(col.cells)]
+    assert got == want
+    assert all(ei.cols[ck].cells[kk].do_ref == (ei.cols[ck].cells[kk].error >= 0.5 * max(want))
+               for ck, col in mesh.cols.items() for kk in col.cells)
+
+
+def test_angular_jump_needs_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    mesh, data, _ = load_golden("c1_uniform")
+    ei = Error_Indicator(Projection(mesh).from_vector(data["u"]))
+    with pytest.raises(RuntimeError):
+        ei.error_angular_jump()

@@ -1,0 +1,111 @@
+"""GPU parity of the AMR error indicators: the device reductions of
+``rtb200_err_angular_jump`` (through ``rt_b200.amr.Error_Indicator``) against the
+reference's own outputs on the golden meshes / solutions (``tests/golden/*.amr.npz``,
+written by the unmodified reference package), and against the oracle restatement on
+seeded fields.  Tolerance 1e-11 relative to the largest entry (FP64 reductions in a
+different order); flags, hp-steering decisions and refined meshes must be identical."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_cases, load_golden
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-11
+FORM = {0: "", 1: "h", 2: "p"}
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    return torch
+
+
+def close(a, b, rtol=TOL):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.max(np.abs(a - b)) <= rtol * max(np.max(np.abs(b)), 1e-300)
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_angular_jump_matches_reference(case, torch_cuda):
+    from rt_b200.amr import Error_Indicator
+    from rt_b200.dg.mesh import from_file as mesh_from_file
+    from rt_b200.dg.projection import Projection
+    mesh, d, _ = load_golden(case)
+    g = dict(np.load(os.path.join(GOLDEN, case + ".amr.npz")))
+    proj = Projection(mesh).from_vector(d["u"])
+    ei = Error_Indicator(proj, ref_kind="all", ref_form="hp", ref_tol=list(g["ref_tol"]))
+    ei.error_angular_jump()
+    order = [(ck, kk) for ck, col in sorted(mesh.cols.items()) for kk in sorted(col.cells)]
+    assert close([ei.cols[ck].cells[kk].error for ck, kk in order], g["aj_cell_err"])
+    assert close([ei.cols[ck].error for ck in sorted(mesh.cols)], g["aj_col_err"])
+    assert close([ei.error, ei.error_to_resolve, ei.col_max_error, ei.cell_max_error],
+                 g["aj_scalars"])
+    # the two integrals behind the hp steering, straight from the device
+    assert close(ei._ixy, g["intg_xy"]) and close(ei._ith, g["intg_th"])
+    assert np.array_equal([ei.cols[ck].cells[kk].do_ref for ck, kk in order], g["aj_cell_ref"])
+    assert [ei.cols[ck].cells[kk].ref_form for ck, kk in order] == \
+        [FORM[int(v)] for v in g["aj_cell_form"]]
+    assert np.array_equal([ei.cols[ck].do_ref for ck in sorted(mesh.cols)], g["aj_col_ref"])
+    assert [ei.cols[ck].ref_form for ck in sorted(mesh.cols)] == \
+        [FORM[int(v)] for v in g["aj_col_form"]]
+    assert ei.ref_by_ind() == mesh_from_file(os.path.join(GOLDEN, case + ".amr_refined.mesh.json"))
+
+
+def test_angular_jump_seeded_field_vs_oracle(torch_cuda):
+    """A rough (random) field on the hp-synthetic mesh and on a 16 x 16 x 32-cell twin of
+    the benchmark mesh: every column / cell size class of the kernel."""
+    from rt_b200 import configs
+    from rt_b200.amr import Error_Indicator
+    from rt_b200.dg.projection import Projection
+    from oracle import amr_oracle as AO
+    rng = np.random.default_rng(11)
+    meshes = [configs.build_mesh([3.0, 2.0], [False, False], [5, 5, 5], nref_ang=5, nref_spt=3),
+              load_golden("test_mesh_script")[0]]
+    for mesh in meshes:
+        u = rng.standard_normal(mesh.get_ndof())
+        ei = Error_Indicator(Projection(mesh).from_vector(u), ref_kind="ang", ref_form="h",
+                             ref_tol=[0.7, 0.0])
+        ei.error_angular_jump()
+        e2 = AO.angular_jump(mesh, u)
+        got = [ei.cols[ck].cells[kk].error for ck, col in sorted(mesh.cols.items())
+               for kk in sorted(col.cells)]
+        assert close(got, np.sqrt(e2))
+        assert close(ei.error, np.sqrt(e2.sum()))
+        assert close(ei._ixy, AO.cell_intg_xy(mesh, u)) and close(ei._ith, AO.col_intg_th(mesh, u))
+
+
+def test_amr_loop_on_the_device_solution(torch_cuda):
+    """solve -> error_angular_jump -> ref_by_ind, three cycles of the 'hp-amr-ang' strategy
+    of experiments/manufactured-solution (input.json: ref_kind ang, ref_form hp, ref_tol
+    [0.9, 0]).  The indicator reads the solution Problem.solve left on the device (no
+    upload), equals the oracle on the returned vector, and the error against the analytic
+    solution does not grow while the mesh does."""
+    from rt_b200 import configs
+    from rt_b200.amr import Error_Indicator
+    from rt_b200.dg.projection import Projection
+    from oracle import amr_oracle as AO
+    mesh = configs.build_mesh([3.0, 2.0], [False, False], [3, 3, 3], nref_ang=2, nref_spt=2)
+    prob, u_exact = configs.manufactured_solution(mesh.Ls)
+    ndofs, errs = [], []
+    for cycle in range(3):
+        uh, conv, _, uvec = prob.solve(mesh, pc_type="none", rtol=1e-11, atol=0.0, max_it=12000,
+                                       return_vector=True)
+        assert conv["converged_reason"] > 0
+        op_solve = uh._device[0]
+        ei = Error_Indicator(uh, ref_kind="ang", ref_form="hp", ref_tol=[0.9, 0.0])
+        assert ei._device_solution()[0] is op_solve
+        ei.error_angular_jump()
+        e2 = AO.angular_jump(mesh, uvec)
+        got = [ei.cols[ck].cells[kk].error for ck, col in sorted(mesh.cols.items())
+               for kk in sorted(col.cells)]
+        assert close(got, np.sqrt(e2), 1e-9)
+        exact = Projection(mesh, u_exact, vectorized=True).to_vector()
+        ndofs.append(mesh.get_ndof())
+        errs.append(np.linalg.norm(uvec - exact) / np.linalg.norm(exact))
+        mesh = ei.ref_by_ind()
+    assert ndofs[0] < ndofs[1] < ndofs[2]
+    assert errs[2] <= errs[0] * 1.5
