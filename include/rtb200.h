@@ -284,6 +284,25 @@ int  rtb200_err_angular_jump(rtb200_ctx* ctx, const double* u_slab_dev,
                              double* cell_err2_dev, double* cell_intg_xy_dev,
                              double* col_intg_th_dev, void* stream);
 
+/* ---- spatial-jump indicator (replaces src/amr/Error_Indicator/error/
+ *      error_spatial_jump.py:30-252): per column, the squared difference of the two
+ *      traces across every face, interpolated to a common quadrature (smaller
+ *      interval, larger node count, in space and in angle) and integrated;
+ *      col_err2[c] = sum / (perimeter * 2 pi).  One launch; single rank.
+ *      Tables (DEVICE pointers, built by rt_b200.amr.spatial_jump):
+ *        sp_off / ap_off / nb [n_col*8]  per (column, face, slot): offset of the spatial
+ *                  block [S0: n0 x nB][S1: n1 x nB][wB: nB][dA] in pool (-1: no
+ *                  neighbour), offset of the (signature, neighbour signature) table in
+ *                  apair, nB
+ *        apair     [ncell0][2][4] per signature pair: (angular block offset in pool | -1,
+ *                  first theta of the neighbour cell, nth1, nH); angular block =
+ *                  [T0: nth0 x nH][T1: nth1 x nH][wH: nH][dG]
+ *      Output: col_err2 [n_col] (device) ------------------------------------ */
+int  rtb200_err_spatial_jump(rtb200_ctx* ctx, const double* u_slab_dev,
+                             const int32_t* sp_off_dev, const int32_t* ap_off_dev,
+                             const int32_t* nb_dev, const double* pool_dev,
+                             const int32_t* apair_dev, double* col_err2_dev, void* stream);
+
 /* ---- instrumentation -------------------------------------------------- */
 int64_t rtb200_launch_count(const rtb200_ctx* ctx);      /* kernels launched so far */
 

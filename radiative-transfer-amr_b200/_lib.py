@@ -91,6 +91,7 @@ SYMBOLS = {
     "rtb200_pc_set_shift": (C.c_int, [C.c_void_p, C.c_double]),
     "rtb200_err_angular_jump": (C.c_int, [C.c_void_p] + [C.c_void_p] * 8 + [C.c_int32]
                                 + [C.c_void_p] * 4),
+    "rtb200_err_spatial_jump": (C.c_int, [C.c_void_p] * 9),
     "rtb200_launch_count": (C.c_int64, [C.c_void_p]),
 }
 

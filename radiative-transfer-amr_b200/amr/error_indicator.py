@@ -135,6 +135,28 @@ def device_angular_jump(op, u_slab):
             ith[:tab.n_nodes].cpu().numpy(), tab)
 
 
+def device_spatial_jump(op, u_slab):
+    """One launch of ``k_err_spatial``; returns the host array ``col_err2 [n_col]``."""
+    import torch
+    from .spatial_jump import SpatialJumpTables
+    tab = getattr(op, "_spatial_jump_tables", None)
+    if tab is None:
+        host = SpatialJumpTables(op.flat)
+
+        def dev(a, dt):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(op.device)
+
+        tab = op._spatial_jump_tables = (dev(host.sp_off, np.int32), dev(host.ap_off, np.int32),
+                                         dev(host.nb, np.int32), dev(host.pool, np.float64),
+                                         dev(host.apair, np.int32))
+    out = torch.empty(max(op.flat.n_col, 1), dtype=torch.float64, device=op.device)
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    op._call("rtb200_err_spatial_jump", op.lib.rtb200_err_spatial_jump(
+        op.ctx, p(u_slab), p(tab[0]), p(tab[1]), p(tab[2]), p(tab[3]), p(tab[4]), p(out),
+        op._stream()))
+    return out[:op.flat.n_col].cpu().numpy()
+
+
 # --------------------------------------------------------------------------- #
 class Error_Indicator:
     def __init__(self, proj: Projection, ref_kind: str = "all", ref_form: str = "hp",
@@ -202,6 +224,29 @@ class Error_Indicator:
         self.cols = cols
         self.col_max_error = col_max_err
         self.cell_max_error = cell_max_err
+        self.error = float(np.sqrt(mesh_err))
+        self._mark()
+
+    def error_spatial_jump(self) -> None:
+        """Mean squared jump of the solution across the spatial faces of every column
+        (``error/error_spatial_jump.py:17-289``); cells carry no error (-INF), as in the
+        reference (``:46-52``)."""
+        op, u_slab = self._device_solution()
+        col_err2 = device_spatial_jump(op, u_slab)
+        cols: dict = {}
+        col_max_err = -consts.INF
+        mesh_err = 0.
+        for c, (col_key, col) in enumerate(sorted(self.proj.cols.items())):
+            assert col.is_lf
+            cells = {cell_key: Error_Indicator_Cell(-consts.INF)
+                     for cell_key, _ in sorted(col.cells.items())}
+            col_err = float(col_err2[c])
+            mesh_err += col_err
+            cols[col_key] = Error_Indicator_Column(float(np.sqrt(col_err)), cells)
+            col_max_err = max(col_max_err, float(np.sqrt(col_err)))
+        self.cols = cols
+        self.col_max_error = col_max_err
+        self.cell_max_error = -consts.INF
         self.error = float(np.sqrt(mesh_err))
         self._mark()
 

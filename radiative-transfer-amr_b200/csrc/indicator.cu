@@ -106,7 +106,109 @@ k_err_angular(DevMesh m, const double* __restrict__ u, const int32_t* __restrict
     }
 }
 
+// ---- spatial jump (error_spatial_jump.py:30-252) ------------------------------------ //
+// One block per column.  Work item = (face F, neighbour slot, own cell K0, overlapping
+// neighbour cell k): a warp takes an item, its lanes the points (p, q) of the common
+// quadrature [nB x nH]; both traces are interpolated there with the pooled Lagrange
+// tables (amr/spatial_jump.py) and the weighted squared difference is accumulated.
+//   col_err2[c] = 1 / (perimeter 2 pi) sum_items (dA dG / 4) sum_pq wB_p wH_q (u0 - u1)^2
+__global__ void __launch_bounds__(EI_THREADS)
+k_err_spatial(DevMesh m, const double* __restrict__ u, const int32_t* __restrict__ sp_off,
+              const int32_t* __restrict__ ap_off, const int32_t* __restrict__ nb_tab,
+              const double* __restrict__ pool, const int32_t* __restrict__ apair,
+              double* __restrict__ col_err2) {
+    __shared__ double s_part[EI_THREADS / 32];
+    const int c = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = EI_THREADS / 32;
+    const int nx = m.col_nx[c], ny = m.col_ny[c];
+    const int sg = m.col_sig[c];
+    const int ntp = m.sig_ntp[sg];
+    const int cell0 = m.sig_cell0[sg], ncell = m.sig_ncell[sg];
+    const double* __restrict__ uc = u + m.col_slab_off[c];
+
+    double acc = 0.0;
+    const int n_items = 8 * ncell * 2;
+    for (int item = warp; item < n_items; item += NW) {
+        const int k = item & 1, K0 = (item >> 1) % ncell, fs = (item >> 1) / ncell;   // fs = F*2 + slot
+        const int F = fs >> 1;
+        const int fidx = c * 8 + fs;
+        const int so = sp_off[fidx];
+        if (so < 0) continue;                               // warp-uniform
+        const int64_t base1 = m.face_base[fidx];
+        if (base1 < 0) continue;                            // (ghost traces: single rank only)
+        const int32_t* __restrict__ ap = apair + ap_off[fidx] + (K0 * 2 + k) * 4;
+        const int ao = ap[0];
+        if (ao < 0) continue;
+        const int tho1 = ap[1], nth1 = ap[2], nH = ap[3];
+        const int nth0 = m.cell_nth[cell0 + K0], tho0 = m.cell_thoff[cell0 + K0];
+        const int n0 = (F & 1) ? nx : ny, n1 = m.face_n1[fidx], nB = nb_tab[fidx];
+        const int rs1 = m.face_rstride[fidx];
+        // own face rows: F = 0: i = nx-1; 1: j = ny-1; 2: i = 0; 3: j = 0
+        const int node0 = F == 0 ? (nx - 1) * ny : (F == 1 ? ny - 1 : 0);
+        const int step0 = (F & 1) ? ny : 1;
+        const double* __restrict__ S0 = pool + so;
+        const double* __restrict__ S1 = S0 + n0 * nB;
+        const double* __restrict__ wB = S1 + n1 * nB;
+        const double dA = wB[nB];
+        const double* __restrict__ T0 = pool + ao;
+        const double* __restrict__ T1 = T0 + nth0 * nH;
+        const double* __restrict__ wH = T1 + nth1 * nH;
+        const double dG = wH[nH];
+        const double* __restrict__ u0 = uc + (int64_t)node0 * ntp + tho0;
+        const double* __restrict__ u1 = u + base1 + tho1;
+        double s = 0.0;
+        for (int e = lane; e < nB * nH; e += 32) {
+            const int p = e / nH, q = e - p * nH;
+            double d = 0.0;
+            for (int j = 0; j < n0; ++j) {
+                const double* __restrict__ row = u0 + (int64_t)j * step0 * ntp;
+                double t = 0.0;
+                for (int a = 0; a < nth0; ++a) t = fma(T0[a * nH + q], row[a], t);
+                d = fma(S0[j * nB + p], t, d);
+            }
+            for (int j = 0; j < n1; ++j) {
+                const double* __restrict__ row = u1 + (int64_t)j * rs1;
+                double t = 0.0;
+                for (int a = 0; a < nth1; ++a) t = fma(T1[a * nH + q], row[a], t);
+                d = fma(-S1[j * nB + p], t, d);
+            }
+            s = fma(wB[p] * wH[q], d * d, s);
+        }
+        acc = fma(0.25 * dA * dG, s, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) s_part[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < NW; ++w) tot += s_part[w];
+        const double perim = 2.0 * m.col_dx[c] + 2.0 * m.col_dy[c];
+        col_err2[c] = tot / (perim * 2.0 * 3.14159265358979323846);
+    }
+}
+
 }  // namespace
+
+extern "C" int rtb200_err_spatial_jump(rtb200_ctx* ctx, const double* u_slab_dev,
+                                       const int32_t* sp_off_dev, const int32_t* ap_off_dev,
+                                       const int32_t* nb_dev, const double* pool_dev,
+                                       const int32_t* apair_dev, double* col_err2_dev,
+                                       void* stream) {
+    if (!ctx) return RTB200_EINVAL;
+    if (!ctx->have_mesh) return rt_fail(ctx, RTB200_ESTATE, "rtb200_err_spatial_jump: no mesh set");
+    if (!u_slab_dev || !sp_off_dev || !ap_off_dev || !nb_dev || !pool_dev || !apair_dev || !col_err2_dev)
+        return rt_fail(ctx, RTB200_EINVAL, "rtb200_err_spatial_jump: null pointer");
+    if (ctx->nranks > 1)
+        return rt_fail(ctx, RTB200_EUNSUPPORTED, "rtb200_err_spatial_jump: single rank only");
+    if (ctx->dm.n_col == 0) return RTB200_OK;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    k_err_spatial<<<ctx->dm.n_col, EI_THREADS, 0, (cudaStream_t)stream>>>(
+        ctx->dm, u_slab_dev, sp_off_dev, ap_off_dev, nb_dev, pool_dev, apair_dev, col_err2_dev);
+    ctx->launches++;
+    RT_CUDA(ctx, cudaGetLastError());
+    return RTB200_OK;
+}
 
 extern "C" int rtb200_err_angular_jump(rtb200_ctx* ctx, const double* u_slab_dev,
                                        const int32_t* cell_lo_dev, const int32_t* cell_up_dev,

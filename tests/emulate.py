@@ -115,3 +115,53 @@ def host_tables(flat, problem):
     g_off, g_pool = build_g_pool(flat, problem.Phi)
     coef = sample_coefficients(flat, problem.kappa, problem.sigma)
     return g_off, g_pool, coef
+
+
+def spatial_jump_emulated(flat, tabs, u_slab):
+    """numpy transliteration of ``k_err_spatial`` (csrc/indicator.cu): walks the same
+    tables with the same index arithmetic on a slab-order vector; returns col_err2."""
+    out = np.zeros(flat.n_col)
+    for c in range(flat.n_col):
+        nx, ny = int(flat.col_nx[c]), int(flat.col_ny[c])
+        sg = int(flat.col_sig[c])
+        ntp = int(flat.sig_ntp[sg])
+        cell0, ncell = int(flat.sig_cell0[sg]), int(flat.sig_ncell[sg])
+        soff = int(flat.col_slab_off[c])
+        acc = 0.0
+        for item in range(8 * ncell * 2):
+            k, K0, fs = item & 1, (item >> 1) % ncell, (item >> 1) // ncell
+            F = fs >> 1
+            fidx = c * 8 + fs
+            so = int(tabs.sp_off[fidx])
+            if so < 0:
+                continue
+            base1 = int(flat.face_base[fidx])
+            if base1 < 0:
+                continue
+            ap = tabs.apair[int(tabs.ap_off[fidx]) + (K0 * 2 + k) * 4:][:4]
+            ao = int(ap[0])
+            if ao < 0:
+                continue
+            tho1, nth1, nH = int(ap[1]), int(ap[2]), int(ap[3])
+            nth0, tho0 = int(flat.cell_nth[cell0 + K0]), int(flat.cell_thoff[cell0 + K0])
+            n0 = nx if (F & 1) else ny
+            n1, nB = int(flat.face_n1[fidx]), int(tabs.nb[fidx])
+            rs1 = int(flat.face_rstride[fidx])
+            node0 = (nx - 1) * ny if F == 0 else (ny - 1 if F == 1 else 0)
+            step0 = ny if (F & 1) else 1
+            P = tabs.pool
+            S0 = P[so:so + n0 * nB].reshape(n0, nB)
+            S1 = P[so + n0 * nB:so + (n0 + n1) * nB].reshape(n1, nB)
+            wB = P[so + (n0 + n1) * nB:][:nB]
+            dA = P[so + (n0 + n1) * nB + nB]
+            T0 = P[ao:ao + nth0 * nH].reshape(nth0, nH)
+            T1 = P[ao + nth0 * nH:ao + (nth0 + nth1) * nH].reshape(nth1, nH)
+            wH = P[ao + (nth0 + nth1) * nH:][:nH]
+            dG = P[ao + (nth0 + nth1) * nH + nH]
+            u0 = np.stack([u_slab[soff + (node0 + j * step0) * ntp + tho0:][:nth0] for j in range(n0)])
+            u1 = np.stack([u_slab[base1 + j * rs1 + tho1:][:nth1] for j in range(n1)])
+            d = S0.T @ u0 @ T0 - S1.T @ u1 @ T1
+            acc += 0.25 * dA * dG * np.sum(wB[:, None] * wH[None, :] * d * d)
+        perim = 2.0 * flat.col_dx[c] + 2.0 * flat.col_dy[c]
+        out[c] = acc / (perim * 2.0 * np.pi)
+    return out

@@ -174,3 +174,19 @@ def test_angular_jump_needs_a_gpu():
     ei = Error_Indicator(Projection(mesh).from_vector(data["u"]))
     with pytest.raises(RuntimeError):
         ei.error_angular_jump()
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_spatial_jump_tables_through_kernel_emulation(case):
+    """The host tables of the device spatial-jump indicator, walked exactly as
+    k_err_spatial walks them (tests/emulate.py), reproduce the reference's column errors."""
+    from emulate import spatial_jump_emulated
+    from rt_b200.amr.spatial_jump import SpatialJumpTables
+    mesh, data, _ = load_golden(case)
+    g = amr_golden(case)
+    flat = FlatMesh(mesh)
+    tabs = SpatialJumpTables(flat)
+    u_slab = np.zeros(flat.n_slab)
+    u_slab[flat.slab_index_of_dof()] = data["u"]
+    e2 = spatial_jump_emulated(flat, tabs, u_slab)
+    assert close(np.sqrt(e2), g["sj_col_err"], 1e-10)

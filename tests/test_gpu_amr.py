@@ -109,3 +109,38 @@ def test_amr_loop_on_the_device_solution(torch_cuda):
         mesh = ei.ref_by_ind()
     assert ndofs[0] < ndofs[1] < ndofs[2]
     assert errs[2] <= errs[0] * 1.5
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_spatial_jump_matches_reference(case, torch_cuda):
+    from rt_b200.amr import Error_Indicator
+    from rt_b200.dg.projection import Projection
+    mesh, d, _ = load_golden(case)
+    g = dict(np.load(os.path.join(GOLDEN, case + ".amr.npz")))
+    ei = Error_Indicator(Projection(mesh).from_vector(d["u"]), ref_kind="spt", ref_form="hp",
+                         ref_tol=list(g["ref_tol"]))
+    ei.error_spatial_jump()
+    cols = sorted(mesh.cols)
+    assert close([ei.cols[ck].error for ck in cols], g["sj_col_err"], 1e-10)
+    assert close([ei.error, ei.error_to_resolve, ei.col_max_error], g["sj_scalars"][:3], 1e-10)
+    assert ei.cell_max_error == g["sj_scalars"][3]            # -INF: cells carry no error
+    assert np.array_equal([ei.cols[ck].do_ref for ck in cols], g["sj_col_ref"])
+    assert [ei.cols[ck].ref_form for ck in cols] == [FORM[int(v)] for v in g["sj_col_form"]]
+
+
+def test_spatial_jump_seeded_field_vs_oracle(torch_cuda):
+    """A rough (random) field on the seeded hp-synthetic mesh (hanging nodes, degree jumps
+    in space and angle, angular h-jumps across columns) and on the hp golden mesh."""
+    from rt_b200 import configs
+    from rt_b200.amr import Error_Indicator
+    from rt_b200.dg.projection import Projection
+    from oracle import amr_oracle as AO
+    rng = np.random.default_rng(12)
+    for m in (configs.hp_synthetic(level=3), load_golden("hp_mixed")[0]):
+        u = rng.standard_normal(m.get_ndof())
+        ei = Error_Indicator(Projection(m).from_vector(u), ref_kind="spt", ref_form="h",
+                             ref_tol=[0.0, 0.7])
+        ei.error_spatial_jump()
+        e2 = AO.spatial_jump(m, u)
+        assert close([ei.cols[ck].error for ck in sorted(m.cols)], np.sqrt(e2), 1e-10)
+        assert close(ei.error, np.sqrt(e2.sum()), 1e-10)
