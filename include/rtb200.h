@@ -239,10 +239,20 @@ int  rtb200_gmres(rtb200_ctx* ctx, const double* b_dev, double* x_dev,
 /* ---- preconditioner: z = mask . (M - S)^{-1} r, the inverse of the reference's
  *      "preconditioner matrix" (preconditioner_matrix.py:22-267, block diagonal
  *      over (column, spatial node)) through the block-circulant structure of the
- *      scattering kernel; uniform angular meshes (>= 8 cells) only, otherwise
- *      RTB200_EUNSUPPORTED.  rtb200_gmres applies it from the left when
+ *      scattering kernel on uniform angular meshes (>= 8 cells), through the eigen
+ *      tables of rtb200_pc_set_eig otherwise (RTB200_EUNSUPPORTED without them).  rtb200_gmres applies it from the left when
  *      params.pc = 1.  x and y must not alias. --------------------------- */
 int  rtb200_pc_apply(rtb200_ctx* ctx, const double* x_slab_dev, double* y_slab_dev, void* stream);
+/* eigen tables of the same preconditioner for angular signatures WITHOUT a block-circulant
+ * table (hp-refined angular meshes, fewer than 8 cells): per signature
+ * [lambda: nt][W: nt x nt][W^T: nt x nt] with D^{-1/2} G D^{-1/2} = Q diag(lambda) Q^T,
+ * W = D^{-1/2} Q, D = diag(th_wt), so that (mk D - ms G)^{-1} = W diag(1/(mk - ms lambda)) W^T
+ * (symmetric scattering kernels; built by rt_b200.rt.tables.pc_eig_tables -- the batched
+ * factorisation of the node blocks reduced to one eigen-decomposition per signature).
+ * sig_eig_off[n_sig]: offset into eig_pool or -1.  HOST pointers, copied.  Call after
+ * rtb200_set_mesh. */
+int  rtb200_pc_set_eig(rtb200_ctx* ctx, const int64_t* sig_eig_off, int32_t n_sig,
+                       const double* eig_pool, int64_t n_pool);
 /* extinction floor kappa_eff = kappa + shift / min(dx, dy) used inside the preconditioner
  * (vacuum regions make M - S singular); default 1, 0 = exact (M - S)^{-1} */
 int  rtb200_pc_set_shift(rtb200_ctx* ctx, double shift);

@@ -89,6 +89,7 @@ SYMBOLS = {
     "rtb200_halo_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "rtb200_pc_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rtb200_pc_set_shift": (C.c_int, [C.c_void_p, C.c_double]),
+    "rtb200_pc_set_eig": (C.c_int, [C.c_void_p, _i64p, C.c_int32, _f64p, C.c_int64]),
     "rtb200_err_angular_jump": (C.c_int, [C.c_void_p] + [C.c_void_p] * 8 + [C.c_int32]
                                 + [C.c_void_p] * 4),
     "rtb200_err_spatial_jump": (C.c_int, [C.c_void_p] * 9),

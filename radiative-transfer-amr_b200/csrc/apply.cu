@@ -508,6 +508,14 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
         std::vector<int32_t> cols, first, count;
         int max_ntp = 0;
         size_t rows_max = 0;
+        size_t pc_rows_nt = 0;
+        int pc_nn = 0;
+        std::vector<int> sigs;
+        void note(int nn, int nt, int sig) {
+            pc_rows_nt = std::max(pc_rows_nt, (size_t)nn * nt);
+            pc_nn = std::max(pc_nn, nn);
+            if (std::find(sigs.begin(), sigs.end(), sig) == sigs.end()) sigs.push_back(sig);
+        }
     };
     // key: (n, -1, 0) dense, (n, sig, mortar?) circulant.  Circulant columns whose faces are
     // all conforming (no hanging node, p- or angular mismatch) go to the persistent kernel
@@ -535,6 +543,7 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
                 a.count.push_back(1);
                 a.cols.push_back(c);
                 a.max_ntp = std::max(a.max_ntp, m->sig_ntp[k.sig]);
+                a.note(nn, m->sig_nt[k.sig], k.sig);
             }
             continue;
         }
@@ -547,6 +556,7 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
             a.rows_max = std::max(a.rows_max, (size_t)((cnt * nn + 7) / 8) * 8);
         }
         a.max_ntp = std::max(a.max_ntp, m->sig_ntp[k.sig]);
+        a.note(nn, m->sig_nt[k.sig], k.sig);
     }
     for (auto& kv : acc) {
         Acc& a = kv.second;
@@ -555,6 +565,9 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
         b.count = (int)a.cols.size();
         b.n_groups = (int)a.first.size();
         b.max_ntp = a.max_ntp;
+        b.pc_max_rows_nt = a.pc_rows_nt;
+        b.pc_max_nn = a.pc_nn;
+        b.sigs = a.sigs;
         if (std::get<1>(kv.first) >= 0) {
             const int sig = std::get<1>(kv.first);
             b.circ_conforming = std::get<2>(kv.first) == 0;
@@ -704,4 +717,5 @@ extern "C" int rtb200_mask(rtb200_ctx* ctx, double* x_slab_dev, int keep, void* 
 }
 
 // node-wise block-Jacobi preconditioner (shares the transforms of k_apply_circ7)
+#include "precond_eig.cuh"
 #include "precond_circ.cuh"

@@ -200,13 +200,26 @@ static int launch_pc_circ(rtb200_ctx* ctx, const Bucket& b, const double* x, dou
     }
 }
 
+// buckets served by the block-circulant kernel; the others use the eigen tables
+static bool pc_circ_bucket(const Bucket& b) {
+    if (b.circ_nc < 8) return false;
+#define X(N_, NC_, P_) if (b.n == N_ && b.circ_nc == NC_ && b.circ_p == P_) return true;
+    RT_CIRC_COMBOS(X)
+#undef X
+    return false;
+}
+
 int rt_pc_setup(rtb200_ctx* ctx, cudaStream_t) {
     if (!ctx->have_mesh) return rt_fail(ctx, RTB200_ESTATE, "no mesh set");
-    for (const Bucket& b : ctx->buckets)
-        if (b.circ_nc < 8)
-            return rt_fail(ctx, RTB200_EUNSUPPORTED,
-                           "the node-wise block-Jacobi preconditioner is built for uniform angular "
-                           "meshes (block-circulant scattering, >= 8 cells) only");
+    for (const Bucket& b : ctx->buckets) {
+        if (pc_circ_bucket(b)) continue;
+        for (int sg : b.sigs)
+            if (ctx->pc_eig_off_host.empty() || ctx->pc_eig_off_host[sg] < 0)
+                return rt_fail(ctx, RTB200_EUNSUPPORTED,
+                               "the node-wise block-Jacobi preconditioner needs, for columns without a "
+                               "uniform angular mesh (>= 8 cells, block-circulant scattering), the "
+                               "eigen tables of rtb200_pc_set_eig (symmetric scattering kernels)");
+    }
     ctx->pc_ready = true;
     return RTB200_OK;
 }
@@ -218,12 +231,16 @@ int rt_pc_apply(rtb200_ctx* ctx, const double* x, double* y, cudaStream_t st) {
     }
     for (const Bucket& b : ctx->buckets) {
         int rc = RTB200_EUNSUPPORTED;
+        if (pc_circ_bucket(b)) {
 #define X(N_, NC_, P_)                                               \
     if (b.n == N_ && b.circ_nc == NC_ && b.circ_p == P_)             \
         rc = launch_pc_circ<N_, NC_, P_>(ctx, b, x, y, st);
-        RT_CIRC_COMBOS(X)
+            RT_CIRC_COMBOS(X)
 #undef X
-        if (rc) return rc == RTB200_EUNSUPPORTED ? rt_fail(ctx, rc, "preconditioner: unsupported bucket") : rc;
+        } else {
+            rc = launch_pc_eig(ctx, b, x, y, st);
+        }
+        if (rc) return rc;
     }
     if (ctx->dm.n_col > 0) {
         k_mask<<<ctx->dm.n_col, 256, 0, st>>>(ctx->dm, y, 1);
@@ -233,7 +250,36 @@ int rt_pc_apply(rtb200_ctx* ctx, const double* x, double* y, cudaStream_t st) {
     return RTB200_OK;
 }
 
-void rt_pc_destroy(rtb200_ctx* ctx) { ctx->pc_ready = false; }
+void rt_pc_destroy(rtb200_ctx* ctx) {
+    ctx->pc_ready = false;
+    ctx->pc_eig_pool = nullptr;        // freed with the other tables (ctx->allocs)
+    ctx->pc_eig_off = nullptr;
+    ctx->pc_eig_off_host.clear();
+}
+
+extern "C" int rtb200_pc_set_eig(rtb200_ctx* ctx, const int64_t* sig_eig_off, int32_t n_sig,
+                                 const double* eig_pool, int64_t n_pool) {
+    if (!ctx) return RTB200_EINVAL;
+    if (!ctx->have_mesh) return rt_fail(ctx, RTB200_ESTATE, "no mesh set (call rtb200_set_mesh first)");
+    if (!sig_eig_off || !eig_pool || n_sig <= 0 || n_pool <= 0)
+        return rt_fail(ctx, RTB200_EINVAL, "pc_set_eig: empty tables");
+    for (int s = 0; s < n_sig; ++s)
+        if (sig_eig_off[s] >= n_pool) return rt_fail(ctx, RTB200_EINVAL, "pc_set_eig: offset outside the pool");
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    double* pool = nullptr;
+    int64_t* off = nullptr;
+    RT_CUDA(ctx, cudaMalloc((void**)&pool, sizeof(double) * (size_t)n_pool));
+    ctx->allocs.push_back(pool);
+    RT_CUDA(ctx, cudaMalloc((void**)&off, sizeof(int64_t) * (size_t)n_sig));
+    ctx->allocs.push_back(off);
+    RT_CUDA(ctx, cudaMemcpy(pool, eig_pool, sizeof(double) * (size_t)n_pool, cudaMemcpyHostToDevice));
+    RT_CUDA(ctx, cudaMemcpy(off, sig_eig_off, sizeof(int64_t) * (size_t)n_sig, cudaMemcpyHostToDevice));
+    ctx->pc_eig_pool = pool;
+    ctx->pc_eig_off = off;
+    ctx->pc_eig_off_host.assign(sig_eig_off, sig_eig_off + n_sig);
+    ctx->pc_ready = false;
+    return RTB200_OK;
+}
 
 extern "C" int rtb200_pc_set_shift(rtb200_ctx* ctx, double shift) {
     if (!ctx) return RTB200_EINVAL;

@@ -48,6 +48,10 @@ struct Bucket {
     bool circ_herm = false;             // every block of the spectrum is Hermitian (symmetric Phi)
     bool circ_conforming = false;       // no mortar face in any column of the bucket
     const double* circ_tab_dev = nullptr;
+    // eigen-table preconditioner (precond_eig.cuh): shared-memory sizing, signatures present
+    size_t pc_max_rows_nt = 0;          // max over columns of nn * nt
+    int pc_max_nn = 0;
+    std::vector<int> sigs;
     std::vector<double> circ_tab_host;  // same table, host copy (kernel parameter of k_apply_circ7)
 };
 
@@ -80,6 +84,9 @@ struct rtb200_ctx {
     int64_t* pc_off = nullptr;     // [n_col]
     bool pc_ready = false;
     double pc_shift = 1.0;         // extinction floor of the preconditioner, in units of 1 / min(dx, dy)
+    double* pc_eig_pool = nullptr; // per-signature eigen tables (rtb200_pc_set_eig), in allocs
+    int64_t* pc_eig_off = nullptr; // [n_sig] device copy
+    std::vector<int64_t> pc_eig_off_host;
 
     // halo / multi-GPU
     int rank = 0, nranks = 1;

@@ -132,6 +132,27 @@ def build_circ_pool(flat: FlatMesh, sig_g_off, g_pool):
     return (np.array(ncs, np.int32), np.array(ps, np.int32), np.array(offs, np.int64), pool)
 
 
+def build_pc_eig_pool(flat: FlatMesh, sig_g_off, g_pool, circ):
+    """Eigen tables (``tables.pc_eig_tables``) of every signature the block-circulant
+    preconditioner does not serve (no circulant table, or fewer than 8 cells).  Returns
+    (off[n_sig] (-1: none), pool)."""
+    offs, parts, n = [], [], 0
+    for si, s in enumerate(flat.arrays.sigs):
+        tab = None
+        if not (circ[2][si] >= 0 and circ[0][si] >= 8):
+            k8 = 8 * ((s.nt + 7) // 8)
+            G = g_pool[sig_g_off[si]: sig_g_off[si] + k8 * k8].reshape(k8, k8)[:s.nt, :s.nt]
+            o = int(flat.sig_th0[si])
+            tab = T.pc_eig_tables(G, flat.th_wt[o:o + s.nt])
+        if tab is None:
+            offs.append(-1)
+        else:
+            offs.append(n)
+            parts.append(tab)
+            n += tab.size
+    return np.array(offs, np.int64), (np.concatenate(parts) if parts else np.zeros(0))
+
+
 class RTOperator:
     """Device-resident operator ``A = (BC - IC) + (M - S)`` for one mesh."""
 
@@ -152,6 +173,7 @@ class RTOperator:
         self.sig_g_off, self.g_pool = build_g_pool(flat, Phi)
         self.coef = sample_coefficients(flat, kappa, sigma)
         self.circ = build_circ_pool(flat, self.sig_g_off, self.g_pool)
+        self.pc_eig = build_pc_eig_pool(flat, self.sig_g_off, self.g_pool, self.circ)
         self._keep = []
         self.ctx = C.c_void_p()
         L.check(self.lib, None, self.lib.rtb200_create(self.device.index or 0, C.byref(self.ctx)),
@@ -203,6 +225,11 @@ class RTOperator:
         put("circ_pool", self.circ[3] if self.circ[3].size else np.zeros(2), np.float64, C.c_double)
         self._call("rtb200_set_mesh", self.lib.rtb200_set_mesh(self.ctx, C.byref(m)))
         keep.clear()
+        off, pool = self.pc_eig
+        if pool.size:
+            self._call("rtb200_pc_set_eig", self.lib.rtb200_pc_set_eig(
+                self.ctx, _as_c(off, C.c_int64), C.c_int32(off.size), _as_c(pool, C.c_double),
+                C.c_int64(pool.size)))
 
     def _call(self, what, rc):
         L.check(self.lib, self.ctx, rc, what)
@@ -292,8 +319,9 @@ class RTOperator:
 
     def pc_apply(self, r_slab, z_slab=None):
         """z = mask . (M - S)^{-1} r on slab-order device tensors: the node-wise
-        block-Jacobi preconditioner (inverse of the reference's ``preconditioner_matrix``,
-        uniform angular meshes only)."""
+        block-Jacobi preconditioner (inverse of the reference's ``preconditioner_matrix``):
+        block-circulant FFT on uniform angular meshes, per-signature eigen tables otherwise
+        (symmetric scattering kernels)."""
         z_slab = self.empty_slab() if z_slab is None else z_slab
         self._call("rtb200_pc_apply", self.lib.rtb200_pc_apply(
             self.ctx, C.c_void_p(r_slab.data_ptr()), C.c_void_p(z_slab.data_ptr()), self._stream()))

@@ -140,6 +140,25 @@ def scattering_kernel(Phi, theta: np.ndarray, wt: np.ndarray) -> np.ndarray:
     return (wt[:, None] * wt[None, :]) * _eval_phi(Phi, theta, theta)
 
 
+def pc_eig_tables(G: np.ndarray, wt: np.ndarray, rtol: float = 1.0e-12):
+    """Tables of the node-wise block-Jacobi preconditioner for one angular signature.
+
+    The blocks of the reference's preconditioner matrix (``preconditioner_matrix.py:154-248``)
+    are ``B_n = mk_n diag(wt) - ms_n G``.  For a symmetric ``G`` (any
+    ``Phi(|theta - theta'|)``) and ``D = diag(wt)``:
+    ``D^{-1/2} G D^{-1/2} = Q diag(lam) Q^T`` and
+    ``B_n^{-1} = W diag(1 / (mk_n - ms_n lam)) W^T`` with ``W = D^{-1/2} Q``.
+    Returns ``concat(lam[nt], W[nt, nt] (row theta), W^T[nt, nt] (row k))`` or ``None``
+    when ``G`` is not symmetric to ``rtol``."""
+    nt = wt.shape[0]
+    if np.max(np.abs(G - G.T)) > rtol * max(np.max(np.abs(G)), 1e-300) or np.any(wt <= 0):
+        return None
+    d = 1.0 / np.sqrt(wt)
+    lam, Q = np.linalg.eigh(0.5 * (G + G.T) * d[:, None] * d[None, :])
+    W = d[:, None] * Q
+    return np.concatenate([lam, W.reshape(-1), np.ascontiguousarray(W.T).reshape(-1)])
+
+
 # --------------------------------------------------------------------------- #
 # block-circulant scattering (uniform angular meshes)
 # --------------------------------------------------------------------------- #

@@ -20,7 +20,8 @@ def torch_cuda():
 
 # unpreconditioned GMRES(50) stagnates on hp_mixed / test_mesh_script (it does so
 # for scipy's GMRES on the reference's own matrix as well); those two cases are
-# solved with the block-Jacobi preconditioner in test_gpu_precond.py
+# left to test_gpu_precond.py (test_mesh_script converges with the node-wise block-Jacobi
+# preconditioner; hp_mixed -- extinction 0..200 on a 28-column mesh -- stagnates with it too)
 UNPRECONDITIONED_OK = [c for c in golden_cases() if c not in ("hp_mixed", "test_mesh_script")]
 
 

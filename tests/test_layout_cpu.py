@@ -242,3 +242,29 @@ def test_hp_synthetic_mesh_tables_reproduce_the_oracle():
         yr = sign * (ref[key] @ x)
         assert rel_err(y, yr) <= 1e-12, (key, rel_err(y, yr))
     assert np.array_equal(f.interior_mask_dof(), ref["mask"].astype(bool))
+
+
+def test_pc_eig_tables_invert_the_preconditioner_blocks():
+    """W diag(1 / (mk - ms lam)) W^T is the inverse of mk diag(wt) - ms G on the hp golden
+    meshes' signatures (host math of the eigen-table preconditioner, precond_eig.cuh)."""
+    from conftest import load_golden
+    from rt_b200.dg.flatmesh import FlatMesh
+    from rt_b200.rt import tables as T
+    for case in ("hp_mixed", "test_mesh_script"):
+        mesh, _, prob = load_golden(case)
+        flat = FlatMesh(mesh)
+        for si, s in enumerate(flat.arrays.sigs):
+            o = int(flat.sig_th0[si])
+            wt = flat.th_wt[o:o + s.nt]
+            G = T.scattering_kernel(prob.Phi, flat.th_theta[o:o + s.nt], wt)
+            tab = T.pc_eig_tables(G, wt)
+            assert tab is not None
+            nt = s.nt
+            lam, W, Wt = tab[:nt], tab[nt:nt + nt * nt].reshape(nt, nt), tab[nt + nt * nt:].reshape(nt, nt)
+            assert np.array_equal(Wt, W.T)
+            for mk, ms in ((3.0, 2.0), (0.4, 0.0), (50.0, 35.0)):
+                B = mk * np.diag(wt) - ms * G
+                Binv = W @ np.diag(1.0 / (mk - ms * lam)) @ W.T
+                assert np.max(np.abs(Binv @ B - np.eye(nt))) < 1e-10
+    # a non-symmetric kernel is refused
+    assert T.pc_eig_tables(G + np.triu(np.ones_like(G), 1) * 1e-3, wt) is None
