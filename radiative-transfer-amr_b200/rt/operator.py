@@ -133,17 +133,16 @@ def build_circ_pool(flat: FlatMesh, sig_g_off, g_pool):
 
 
 def build_pc_eig_pool(flat: FlatMesh, sig_g_off, g_pool, circ):
-    """Eigen tables (``tables.pc_eig_tables``) of every signature the block-circulant
-    preconditioner does not serve (no circulant table, or fewer than 8 cells).  Returns
-    (off[n_sig] (-1: none), pool)."""
+    """Eigen tables (``tables.pc_eig_tables``) of every signature with a symmetric
+    scattering kernel.  The library uses them for the columns its block-circulant
+    preconditioner kernel does not serve (no circulant table, fewer than 8 cells, or an
+    (N, NC, P) combination it is not compiled for).  Returns (off[n_sig] (-1: none), pool)."""
     offs, parts, n = [], [], 0
     for si, s in enumerate(flat.arrays.sigs):
-        tab = None
-        if not (circ[2][si] >= 0 and circ[0][si] >= 8):
-            k8 = 8 * ((s.nt + 7) // 8)
-            G = g_pool[sig_g_off[si]: sig_g_off[si] + k8 * k8].reshape(k8, k8)[:s.nt, :s.nt]
-            o = int(flat.sig_th0[si])
-            tab = T.pc_eig_tables(G, flat.th_wt[o:o + s.nt])
+        k8 = 8 * ((s.nt + 7) // 8)
+        G = g_pool[sig_g_off[si]: sig_g_off[si] + k8 * k8].reshape(k8, k8)[:s.nt, :s.nt]
+        o = int(flat.sig_th0[si])
+        tab = T.pc_eig_tables(G, flat.th_wt[o:o + s.nt])
         if tab is None:
             offs.append(-1)
         else:
