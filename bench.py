@@ -512,6 +512,33 @@ def run_b200(args):
         except Exception as exc:      # report, do not hide
             gm = {"error": str(exc)} if gm is None else {**gm, "error": str(exc)}
 
+    # ---- AMR error indicators on the resident vector (one launch each) -------- #
+    amr = None
+    if not args.no_amr:
+        try:
+            from rt_b200.amr.error_indicator import device_angular_jump, device_spatial_jump
+            amr = {}
+            t = time.perf_counter()
+            device_angular_jump(op, x, to_host=False)            # builds + uploads the tables
+            torch.cuda.synchronize(dev)
+            amr["angular_jump_tables_s"] = time.perf_counter() - t
+            k = max(3, args.steps // 4)
+            ms = timed(lambda: device_angular_jump(op, x, to_host=False), k) / k
+            amr["angular_jump"] = {"ms": ms, "kernel": "k_err_angular",
+                                   "algorithmic_bytes_per_dof": 8.0,
+                                   "achieved_gbs": 8.0 * (n_total / world) / (ms * 1e-3) / 1e9,
+                                   "frac_hbm": 8.0 * (n_total / world) / (ms * 1e-3) / 1e9 / hbm_peak}
+            if world == 1:
+                t = time.perf_counter()
+                device_spatial_jump(op, x, to_host=False)
+                torch.cuda.synchronize(dev)
+                amr["spatial_jump_tables_s"] = time.perf_counter() - t
+                ms = timed(lambda: device_spatial_jump(op, x, to_host=False), k) / k
+                amr["spatial_jump"] = {"ms": ms, "kernel": "k_err_spatial",
+                                       "note": "reads face rows only; L1/L2-bound interpolation"}
+        except Exception as exc:      # report, do not hide
+            amr = {**(amr or {}), "error": str(exc)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
@@ -539,7 +566,7 @@ def run_b200(args):
                                  % (op.n_slab * 8 / 1e9),
                            "table_build_s": t_build},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-                "e2e": e2e, "gmres": gm, "cpu_baseline": cpu}
+                "e2e": e2e, "gmres": gm, "amr_indicators": amr, "cpu_baseline": cpu}
         print(json.dumps(line))
     op.close()
     if world > 1:
@@ -557,6 +584,7 @@ def main():
     ap.add_argument("--no-gmres", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-solve", action="store_true", help="skip the GMRES time-to-solve runs")
+    ap.add_argument("--no-amr", action="store_true", help="skip the error-indicator kernel timings")
     ap.add_argument("--solve-max-it", type=int, default=200)
     ap.add_argument("--dense-scattering", action="store_true",
                     help="force the dense (DMMA) scattering product even on uniform angular meshes")

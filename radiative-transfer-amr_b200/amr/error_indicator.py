@@ -115,9 +115,10 @@ class IndicatorTables:
         self.col_th_off_dev = dev(self.col_th_off if nt.size else np.zeros(1), np.int64)
 
 
-def device_angular_jump(op, u_slab):
-    """One launch of ``k_err_angular``.  Returns host arrays
-    ``(cell_err2 [cells], intg_xy [angles], intg_th [nodes])`` in column order."""
+def device_angular_jump(op, u_slab, to_host: bool = True):
+    """One launch of ``k_err_angular``.  Returns
+    ``(cell_err2 [cells], intg_xy [angles], intg_th [nodes], tables)`` in column order, as
+    host arrays (``to_host``) or as the device tensors the kernel wrote."""
     import torch
     tab = getattr(op, "_indicator_tables", None)
     if tab is None:
@@ -131,12 +132,15 @@ def device_angular_jump(op, u_slab):
         op.ctx, p(u_slab), p(tab.cell_lo), p(tab.cell_up), p(tab.lag_bot), p(tab.lag_top),
         p(tab.lgl_w), p(tab.col_cell_off_dev), p(tab.col_th_off_dev),
         C.c_int32(tab.max_cell_nodes), p(err2), p(ixy), p(ith), op._stream()))
+    if not to_host:
+        return err2, ixy, ith, tab
     return (err2[:tab.n_cells].cpu().numpy(), ixy[:tab.n_theta].cpu().numpy(),
             ith[:tab.n_nodes].cpu().numpy(), tab)
 
 
-def device_spatial_jump(op, u_slab):
-    """One launch of ``k_err_spatial``; returns the host array ``col_err2 [n_col]``."""
+def device_spatial_jump(op, u_slab, to_host: bool = True):
+    """One launch of ``k_err_spatial``; returns ``col_err2 [n_col]`` (host array, or the
+    device tensor when ``to_host`` is False)."""
     import torch
     from .spatial_jump import SpatialJumpTables
     tab = getattr(op, "_spatial_jump_tables", None)
@@ -154,7 +158,7 @@ def device_spatial_jump(op, u_slab):
     op._call("rtb200_err_spatial_jump", op.lib.rtb200_err_spatial_jump(
         op.ctx, p(u_slab), p(tab[0]), p(tab[1]), p(tab[2]), p(tab[3]), p(tab[4]), p(out),
         op._stream()))
-    return out[:op.flat.n_col].cpu().numpy()
+    return out[:op.flat.n_col].cpu().numpy() if to_host else out
 
 
 # --------------------------------------------------------------------------- #
