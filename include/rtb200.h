@@ -313,6 +313,24 @@ int  rtb200_err_spatial_jump(rtb200_ctx* ctx, const double* u_slab_dev,
                              const int32_t* nb_dev, const double* pool_dev,
                              const int32_t* apair_dev, double* col_err2_dev, void* stream);
 
+/* ---- high-resolution error (replaces the cell loops of src/amr/Error_Indicator/error/
+ *      error_high_resolution.py:83-216): ctx_lo / ctx_hi hold a mesh and a p-refined copy of
+ *      it (same columns and cells, more nodes: ref_mesh(form = "p")); the low-resolution
+ *      solution is interpolated to the high-resolution nodes and compared there:
+ *        cell_err2[cells] = (dx dy dth / 8) sum w (u_hi - I u_lo)^2      (:194-205)
+ *        col_hr2[n_col]   = sum over the column's cells of (dx dy / 4)(dth / 2) sum w u_hi^2 (:83-113)
+ *      Tables (DEVICE pointers): lgl_ip_off [(MAX_NXY+1)^2] / lg_ip_off [(MAX_NTH+1)^2] offsets
+ *      into ip_pool of the [n][m] Lagrange interpolation from n to m nodes; lgl_w
+ *      [(MAX_NXY+1)][MAX_NXY], lg_w [(MAX_NTH+1)][MAX_NTH] weights; cell_dth [n_sigcell of
+ *      ctx_lo] cell widths; col_cell_off [n_col]; max_cell_dofs = largest low-resolution cell. */
+int  rtb200_err_high_resolution(rtb200_ctx* ctx_lo, const double* u_lo_slab_dev,
+                                rtb200_ctx* ctx_hi, const double* u_hi_slab_dev,
+                                const int32_t* lgl_ip_off_dev, const int32_t* lg_ip_off_dev,
+                                const double* ip_pool_dev, const double* lgl_w_dev,
+                                const double* lg_w_dev, const double* cell_dth_dev,
+                                const int64_t* col_cell_off_dev, int32_t max_cell_dofs,
+                                double* cell_err2_dev, double* col_hr2_dev, void* stream);
+
 /* ---- instrumentation -------------------------------------------------- */
 int64_t rtb200_launch_count(const rtb200_ctx* ctx);      /* kernels launched so far */
 

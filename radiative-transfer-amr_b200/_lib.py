@@ -93,6 +93,7 @@ SYMBOLS = {
     "rtb200_err_angular_jump": (C.c_int, [C.c_void_p] + [C.c_void_p] * 8 + [C.c_int32]
                                 + [C.c_void_p] * 4),
     "rtb200_err_spatial_jump": (C.c_int, [C.c_void_p] * 9),
+    "rtb200_err_high_resolution": (C.c_int, [C.c_void_p] * 11 + [C.c_int32] + [C.c_void_p] * 3),
     "rtb200_launch_count": (C.c_int64, [C.c_void_p]),
 }
 

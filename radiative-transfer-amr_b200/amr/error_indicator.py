@@ -161,6 +161,93 @@ def device_spatial_jump(op, u_slab, to_host: bool = True):
     return out[:op.flat.n_col].cpu().numpy() if to_host else out
 
 
+_IP_TABLES = None
+
+
+def interpolation_tables():
+    """Lagrange interpolation from n to m >= n nodes, all pairs: LGL (space) and LG (angle)
+    (``error_high_resolution.py:131-156,181-192``: ``phi_proj[ii, pp] = lag_eval(xxb, ii,
+    xxb_hr[pp])``).  Returns (lgl_off[(MAX_NXY+1)^2], lg_off[(MAX_NTH+1)^2], pool, lg_w, lgl_w);
+    the weight tables hold every order (a FlatMesh only carries the orders of its mesh)."""
+    global _IP_TABLES
+    if _IP_TABLES is None:
+        from ..dg.quadrature import lag_eval_table
+        parts, n_pool = [], 0
+        lgl_off = -np.ones((L.MAX_NXY + 1, L.MAX_NXY + 1), np.int32)
+        lg_off = -np.ones((L.MAX_NTH + 1, L.MAX_NTH + 1), np.int32)
+        lg_w = np.zeros((L.MAX_NTH + 1, L.MAX_NTH))
+        for off, nmax, which in ((lgl_off, L.MAX_NXY, 0), (lg_off, L.MAX_NTH, 4)):
+            for n in range(1, nmax + 1):
+                lo = np.asarray(quad_xyth(**{("nnodes_x", "nnodes_th")[which // 4]: n})[which])
+                for m in range(n, nmax + 1):
+                    hi = np.asarray(quad_xyth(**{("nnodes_x", "nnodes_th")[which // 4]: m})[which])
+                    off[n, m] = n_pool
+                    parts.append(lag_eval_table(lo, hi).reshape(-1))
+                    n_pool += n * m
+        for n in range(1, L.MAX_NTH + 1):
+            lg_w[n, :n] = quad_xyth(nnodes_th=n)[5]
+        lgl_w = np.zeros((L.MAX_NXY + 1, L.MAX_NXY))
+        for n in range(1, L.MAX_NXY + 1):
+            lgl_w[n, :n] = quad_xyth(nnodes_x=n)[1]
+        _IP_TABLES = (lgl_off.reshape(-1), lg_off.reshape(-1), np.concatenate(parts), lg_w, lgl_w)
+    return _IP_TABLES
+
+
+def device_high_resolution(op_lo, u_lo, op_hi, u_hi):
+    """One launch of ``k_err_hires``: per-cell squared error of the low-resolution solution
+    against the high-resolution one (same columns and cells, more nodes), and the per-column
+    squared norm of the latter.  Host arrays ``(cell_err2 [cells], col_hr2 [n_col])``."""
+    import torch
+    fl, fh = op_lo.flat, op_hi.flat
+    if fl.n_col != fh.n_col or not np.array_equal(fl.sig_ncell[fl.col_sig], fh.sig_ncell[fh.col_sig]) \
+            or np.any(fl.col_nx > fh.col_nx) or np.any(fl.col_ny > fh.col_ny):
+        raise ValueError("error_high_resolution: the high-resolution mesh must be a p-refinement "
+                         "of the projection's mesh (same columns and cells)")
+    for sl, sh in set(zip(fl.col_sig.tolist(), fh.col_sig.tolist())):
+        a, b = fl.arrays.sigs[sl], fh.arrays.sigs[sh]
+        if not np.array_equal(a.keys, b.keys) or np.any(a.nth > b.nth):
+            raise ValueError("error_high_resolution: angular cells of the two meshes differ")
+    lgl_off, lg_off, pool, lg_w, lgl_w = interpolation_tables()
+    ncell = fl.sig_ncell[fl.col_sig].astype(np.int64)
+    col_cell_off = np.concatenate([[0], np.cumsum(ncell)[:-1]]).astype(np.int64)
+    dth = np.concatenate([np.asarray(s.th1) - np.asarray(s.th0) for s in fl.arrays.sigs])
+    max_nth = np.array([int(s.nth.max()) for s in fl.arrays.sigs])
+    max_cell = int((fl.col_nx.astype(np.int64) * fl.col_ny * max_nth[fl.col_sig]).max())
+
+    def dev(a, dt):
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(op_lo.device)
+
+    t = [dev(lgl_off, np.int32), dev(lg_off, np.int32), dev(pool, np.float64),
+         dev(lgl_w, np.float64), dev(lg_w, np.float64), dev(dth, np.float64),
+         dev(col_cell_off, np.int64)]
+    n_cells = int(ncell.sum())
+    err2 = torch.empty(max(n_cells, 1), dtype=torch.float64, device=op_lo.device)
+    hr2 = torch.empty(max(fl.n_col, 1), dtype=torch.float64, device=op_lo.device)
+    p = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+    op_lo._call("rtb200_err_high_resolution", op_lo.lib.rtb200_err_high_resolution(
+        op_lo.ctx, p(u_lo), op_hi.ctx, p(u_hi), *[p(x) for x in t], C.c_int32(max_cell),
+        p(err2), p(hr2), op_lo._stream()))
+    return err2[:n_cells].cpu().numpy(), hr2[:fl.n_col].cpu().numpy()
+
+
+def device_solution(proj):
+    """(operator, slab-order device vector) of a projection: the pair ``Problem.solve`` left
+    on it, else a table-only operator for its mesh and an upload of its values."""
+    dev = getattr(proj, "_device", None)
+    if dev is not None:
+        op, u_slab = dev
+        if getattr(op, "ctx", None) is not None and op.ctx.value and \
+                op.flat.nranks == 1 and op.n == proj.mesh.get_ndof():
+            return op, u_slab
+    from ..rt.operator import RTOperator
+    zero = lambda x, y: np.zeros(np.broadcast(x, y).shape)          # noqa: E731
+    iso = lambda th0, th1: 1. / (2. * consts.PI) + 0. * (th0 - th1)  # noqa: E731
+    op = RTOperator(proj.mesh, zero, zero, iso)
+    u_slab = op.to_slab(proj.to_vector())
+    proj._device = (op, u_slab)
+    return op, u_slab
+
+
 # --------------------------------------------------------------------------- #
 class Error_Indicator:
     def __init__(self, proj: Projection, ref_kind: str = "all", ref_form: str = "hp",
@@ -174,22 +261,7 @@ class Error_Indicator:
 
     # ---- device state ---------------------------------------------------- #
     def _device_solution(self):
-        """(operator, slab-order device vector) of ``self.proj``: the pair
-        ``Problem.solve`` left on the projection, else a table-only operator for
-        the projection's mesh and an upload of its values."""
-        dev = getattr(self.proj, "_device", None)
-        if dev is not None:
-            op, u_slab = dev
-            if getattr(op, "ctx", None) is not None and op.ctx.value and \
-                    op.flat.nranks == 1 and op.n == self.proj.mesh.get_ndof():
-                return op, u_slab
-        from ..rt.operator import RTOperator
-        zero = lambda x, y: np.zeros(np.broadcast(x, y).shape)          # noqa: E731
-        iso = lambda th0, th1: 1. / (2. * consts.PI) + 0. * (th0 - th1)  # noqa: E731
-        op = RTOperator(self.proj.mesh, zero, zero, iso)
-        u_slab = op.to_slab(self.proj.to_vector())
-        self.proj._device = (op, u_slab)
-        return op, u_slab
+        return device_solution(self.proj)
 
     # ---- indicators -------------------------------------------------------- #
     def error_angular_jump(self) -> None:
@@ -253,6 +325,61 @@ class Error_Indicator:
         self.cell_max_error = -consts.INF
         self.error = float(np.sqrt(mesh_err))
         self._mark()
+
+    def error_high_resolution(self, problem, uh_hr: Projection = None, **kwargs) -> list:
+        """Relative L2 error against the solution on a p-refined copy of the mesh
+        (``error/error_high_resolution.py:26-271``): the high-resolution solve runs through
+        ``problem.solve`` (the GPU solver), the interpolation of the low-resolution solution
+        to the high-resolution nodes and both integrals in one kernel launch.  Returns
+        ``[uh_hr, info, mat_info]`` like the reference."""
+        opts = {"ang_ref_offset": 0, "spt_ref_offset": 0, "ksp_type": "gmres",
+                "pc_type": "bjacobi", "verbose": False, "blocking": True, **kwargs}
+        if uh_hr is None:
+            mesh_hr = copy.deepcopy(self.proj.mesh)
+            for _ in range(0, opts["ang_ref_offset"]):
+                mesh_hr.ref_mesh(kind="ang", form="p")
+            for _ in range(0, opts["spt_ref_offset"]):
+                mesh_hr.ref_mesh(kind="spt", form="p")
+            extra = {k: v for k, v in opts.items() if k in ("rtol", "atol", "max_it", "restart")}
+            [uh_hr, info, mat_info] = problem.solve(mesh_hr, ksp_type=opts["ksp_type"],
+                                                    pc_type=opts["pc_type"], **extra)
+        else:
+            info = None
+            mat_info = None
+        op_hi, u_hi = device_solution(uh_hr)
+        op_lo, u_lo = self._device_solution()
+        cell_err2, col_hr2 = device_high_resolution(op_lo, u_lo, op_hi, u_hi)
+        intg_uh_hr2 = 0.
+        for v in col_hr2:
+            intg_uh_hr2 += float(v)
+
+        cols: dict = {}
+        col_max_err = -consts.INF
+        cell_max_err = -consts.INF
+        mesh_err = 0.
+        k = 0
+        for col_key, col in sorted(self.proj.cols.items()):
+            assert col.is_lf
+            cells: dict = {}
+            col_err = 0.
+            for cell_key, cell in sorted(col.cells.items()):
+                assert cell.is_lf
+                e2 = float(cell_err2[k])
+                k += 1
+                col_err += e2
+                mesh_err += e2
+                err = float(np.sqrt(e2 / intg_uh_hr2))
+                cells[cell_key] = Error_Indicator_Cell(err)
+                cell_max_err = max(cell_max_err, err)
+            cols[col_key] = Error_Indicator_Column(float(np.sqrt(col_err / intg_uh_hr2)), cells)
+            col_max_err = max(col_max_err, cols[col_key].error)
+        self.cols = cols
+        self.col_max_error = col_max_err
+        self.cell_max_error = cell_max_err
+        self.error = float(np.sqrt(mesh_err / intg_uh_hr2))
+        self._intg_xy = self._intg_th = None       # hp steering from the projection's values
+        self._mark()
+        return [uh_hr, info, mat_info]
 
     def error_random(self, rng=None) -> None:
         """Uniform random indicator per cell (``error/error_random.py:15-91``)."""

@@ -188,7 +188,127 @@ k_err_spatial(DevMesh m, const double* __restrict__ u, const int32_t* __restrict
     }
 }
 
+// ---- high-resolution error (error_high_resolution.py:83-216) --------------------------- //
+// The low-resolution solution interpolated to the nodes of a p-refined copy of the same
+// mesh (same columns and cells, more nodes: ref_mesh(form = "p")), compared there with the
+// high-resolution solution:
+//   cell_err2[c][K] = (dx dy dth / 8) sum_pqr w_p w_q w_r (u_hr - sum_ija phi_ip psi_jq xsi_ar u_ija)^2
+//   col_hr2[c]      = (dx dy / 4) sum_K (dth / 2) sum_pqr w_p w_q w_r u_hr^2     (the norm, :83-113)
+// One block per column, the cells one after the other: the low-resolution cell is staged in
+// shared memory, a thread owns high-resolution nodes (p, q, r); block reduction in a fixed
+// order.  mlo / mhi: the two meshes' device tables (columns and cells correspond one to one).
+__global__ void __launch_bounds__(EI_THREADS)
+k_err_hires(DevMesh mlo, DevMesh mhi, const double* __restrict__ ulo, const double* __restrict__ uhi,
+            const int32_t* __restrict__ lgl_ip_off, const int32_t* __restrict__ lg_ip_off,
+            const double* __restrict__ ip_pool, const double* __restrict__ lgl_w,
+            const double* __restrict__ lg_w, const double* __restrict__ cell_dth,
+            const int64_t* __restrict__ col_cell_off, double* __restrict__ cell_err2,
+            double* __restrict__ col_hr2) {
+    extern __shared__ __align__(16) double hr_s[];
+    __shared__ double s_red[2][EI_THREADS / 32];
+    const int c = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = EI_THREADS / 32;
+    const int nx = mlo.col_nx[c], ny = mlo.col_ny[c];
+    const int px = mhi.col_nx[c], py = mhi.col_ny[c];
+    const int sgl = mlo.col_sig[c], sgh = mhi.col_sig[c];
+    const int ntpl = mlo.sig_ntp[sgl], ntph = mhi.sig_ntp[sgh];
+    const int cl0 = mlo.sig_cell0[sgl], ch0 = mhi.sig_cell0[sgh], ncell = mlo.sig_ncell[sgl];
+    const double* __restrict__ ul = ulo + mlo.col_slab_off[c];
+    const double* __restrict__ uh = uhi + mhi.col_slab_off[c];
+    const double* __restrict__ phi = ip_pool + lgl_ip_off[nx * (RT_MAXN + 1) + px];   // [nx][px]
+    const double* __restrict__ psi = ip_pool + lgl_ip_off[ny * (RT_MAXN + 1) + py];   // [ny][py]
+    const double* __restrict__ wx = lgl_w + px * RT_MAXN;
+    const double* __restrict__ wy = lgl_w + py * RT_MAXN;
+    const double dxy = mlo.col_dx[c] * mlo.col_dy[c];
+    double hr2_col = 0.0;
+    for (int K = 0; K < ncell; ++K) {
+        const int nth = mlo.cell_nth[cl0 + K], thol = mlo.cell_thoff[cl0 + K];
+        const int pth = mhi.cell_nth[ch0 + K], thoh = mhi.cell_thoff[ch0 + K];
+        const double* __restrict__ xsi = ip_pool + lg_ip_off[nth * (RTB200_MAX_NTH + 1) + pth];   // [nth][pth]
+        const double* __restrict__ wth = lg_w + pth * RTB200_MAX_NTH;
+        const double dth = cell_dth[cl0 + K];
+        __syncthreads();                                   // previous cell's reads of hr_s are done
+        for (int e = tid; e < nx * ny * nth; e += EI_THREADS) {
+            const int n = e / nth, a = e - n * nth;
+            hr_s[e] = ul[(int64_t)n * ntpl + thol + a];
+        }
+        __syncthreads();
+        double s_err = 0.0, s_hr2 = 0.0;
+        for (int e = tid; e < px * py * pth; e += EI_THREADS) {
+            const int pq = e / pth, r = e - pq * pth;
+            const int p = pq / py, q = pq - p * py;
+            double v = 0.0;
+            for (int i = 0; i < nx; ++i) {
+                double vi = 0.0;
+                for (int j = 0; j < ny; ++j) {
+                    const double* __restrict__ row = hr_s + (i * ny + j) * nth;
+                    double vj = 0.0;
+                    for (int a = 0; a < nth; ++a) vj = fma(xsi[a * pth + r], row[a], vj);
+                    vi = fma(psi[j * py + q], vj, vi);
+                }
+                v = fma(phi[i * px + p], vi, v);
+            }
+            const double h = uh[(int64_t)pq * ntph + thoh + r];
+            const double w = wx[p] * wy[q] * wth[r];
+            s_err = fma(w, (h - v) * (h - v), s_err);
+            s_hr2 = fma(w, h * h, s_hr2);
+        }
+        s_err = warp_sum(s_err);
+        s_hr2 = warp_sum(s_hr2);
+        if (lane == 0) {
+            s_red[0][warp] = s_err;
+            s_red[1][warp] = s_hr2;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double te = 0.0, th2 = 0.0;
+            for (int w = 0; w < NW; ++w) {
+                te += s_red[0][w];
+                th2 += s_red[1][w];
+            }
+            cell_err2[col_cell_off[c] + K] = 0.125 * dxy * dth * te;
+            hr2_col += 0.25 * dxy * (0.5 * dth) * th2;
+        }
+    }
+    if (tid == 0) col_hr2[c] = hr2_col;
+}
+
 }  // namespace
+
+extern "C" int rtb200_err_high_resolution(rtb200_ctx* ctx_lo, const double* u_lo_slab_dev,
+                                          rtb200_ctx* ctx_hi, const double* u_hi_slab_dev,
+                                          const int32_t* lgl_ip_off_dev, const int32_t* lg_ip_off_dev,
+                                          const double* ip_pool_dev, const double* lgl_w_dev,
+                                          const double* lg_w_dev, const double* cell_dth_dev,
+                                          const int64_t* col_cell_off_dev, int32_t max_cell_dofs,
+                                          double* cell_err2_dev, double* col_hr2_dev, void* stream) {
+    if (!ctx_lo || !ctx_hi) return RTB200_EINVAL;
+    rtb200_ctx* ctx = ctx_lo;
+    if (!ctx_lo->have_mesh || !ctx_hi->have_mesh)
+        return rt_fail(ctx, RTB200_ESTATE, "rtb200_err_high_resolution: no mesh set");
+    if (!u_lo_slab_dev || !u_hi_slab_dev || !lgl_ip_off_dev || !lg_ip_off_dev || !ip_pool_dev ||
+        !lgl_w_dev || !lg_w_dev || !cell_dth_dev || !col_cell_off_dev || !cell_err2_dev || !col_hr2_dev)
+        return rt_fail(ctx, RTB200_EINVAL, "rtb200_err_high_resolution: null pointer");
+    if (ctx_lo->dm.n_col != ctx_hi->dm.n_col || ctx_lo->device != ctx_hi->device)
+        return rt_fail(ctx, RTB200_EINVAL,
+                       "rtb200_err_high_resolution: the two meshes must have the same columns, on one device");
+    if (ctx_lo->nranks > 1 || ctx_hi->nranks > 1)
+        return rt_fail(ctx, RTB200_EUNSUPPORTED, "rtb200_err_high_resolution: single rank only");
+    if (max_cell_dofs <= 0 || (size_t)max_cell_dofs * sizeof(double) > 200 * 1024)
+        return rt_fail(ctx, RTB200_EUNSUPPORTED, "rtb200_err_high_resolution: cell too large for shared memory");
+    if (ctx->dm.n_col == 0) return RTB200_OK;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t smem = sizeof(double) * (size_t)max_cell_dofs;
+    if (smem > 48 * 1024)
+        RT_CUDA(ctx, cudaFuncSetAttribute(k_err_hires, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_err_hires<<<ctx->dm.n_col, EI_THREADS, smem, (cudaStream_t)stream>>>(
+        ctx_lo->dm, ctx_hi->dm, u_lo_slab_dev, u_hi_slab_dev, lgl_ip_off_dev, lg_ip_off_dev, ip_pool_dev,
+        lgl_w_dev, lg_w_dev, cell_dth_dev, col_cell_off_dev, cell_err2_dev, col_hr2_dev);
+    ctx->launches++;
+    RT_CUDA(ctx, cudaGetLastError());
+    return RTB200_OK;
+}
 
 extern "C" int rtb200_err_spatial_jump(rtb200_ctx* ctx, const double* u_slab_dev,
                                        const int32_t* sp_off_dev, const int32_t* ap_off_dev,

@@ -165,3 +165,38 @@ def spatial_jump_emulated(flat, tabs, u_slab):
         perim = 2.0 * flat.col_dx[c] + 2.0 * flat.col_dy[c]
         out[c] = acc / (perim * 2.0 * np.pi)
     return out
+
+
+def high_resolution_emulated(flat_lo, u_lo, flat_hi, u_hi, tables):
+    """numpy transliteration of ``k_err_hires`` (csrc/indicator.cu) on slab-order vectors;
+    ``tables`` = ``rt_b200.amr.error_indicator.interpolation_tables()``.  Returns
+    (cell_err2 [cells], col_hr2 [n_col])."""
+    lgl_off, lg_off, pool, lg_w, lgl_w = tables
+    MX, MT = 12, 16
+    err2, hr2 = [], np.zeros(flat_lo.n_col)
+    dth_all = np.concatenate([np.asarray(s.th1) - np.asarray(s.th0) for s in flat_lo.arrays.sigs])
+    for c in range(flat_lo.n_col):
+        nx, ny = int(flat_lo.col_nx[c]), int(flat_lo.col_ny[c])
+        px, py = int(flat_hi.col_nx[c]), int(flat_hi.col_ny[c])
+        sgl, sgh = int(flat_lo.col_sig[c]), int(flat_hi.col_sig[c])
+        ntpl, ntph = int(flat_lo.sig_ntp[sgl]), int(flat_hi.sig_ntp[sgh])
+        cl0, ch0 = int(flat_lo.sig_cell0[sgl]), int(flat_hi.sig_cell0[sgh])
+        ul = u_lo[int(flat_lo.col_slab_off[c]):]
+        uh = u_hi[int(flat_hi.col_slab_off[c]):]
+        o = int(lgl_off[nx * (MX + 1) + px]); phi = pool[o:o + nx * px].reshape(nx, px)
+        o = int(lgl_off[ny * (MX + 1) + py]); psi = pool[o:o + ny * py].reshape(ny, py)
+        wx, wy = lgl_w[px, :px], lgl_w[py, :py]
+        dxy = flat_lo.col_dx[c] * flat_lo.col_dy[c]
+        for K in range(int(flat_lo.sig_ncell[sgl])):
+            nth, thol = int(flat_lo.cell_nth[cl0 + K]), int(flat_lo.cell_thoff[cl0 + K])
+            pth, thoh = int(flat_hi.cell_nth[ch0 + K]), int(flat_hi.cell_thoff[ch0 + K])
+            o = int(lg_off[nth * (MT + 1) + pth]); xsi = pool[o:o + nth * pth].reshape(nth, pth)
+            wth = lg_w[pth, :pth]
+            lo = np.stack([ul[n * ntpl + thol:][:nth] for n in range(nx * ny)]).reshape(nx, ny, nth)
+            hi = np.stack([uh[n * ntph + thoh:][:pth] for n in range(px * py)]).reshape(px, py, pth)
+            v = np.einsum("ija,ip,jq,ar->pqr", lo, phi, psi, xsi)
+            w = wx[:, None, None] * wy[None, :, None] * wth[None, None, :]
+            dth = dth_all[cl0 + K]
+            err2.append(0.125 * dxy * dth * np.sum(w * (hi - v) ** 2))
+            hr2[c] += 0.25 * dxy * (0.5 * dth) * np.sum(w * hi * hi)
+    return np.array(err2), hr2

@@ -14,9 +14,14 @@ spelled ``Error_Indicator``) computes
   cell / column errors, refinement flags, hp-steering decisions, and the mesh
   ``ref_by_ind`` returns;
 * ``error_spatial_jump`` (same settings): column errors and flags;
-* ``cell_intg_xy`` / ``col_intg_th`` of every cell / column.
+* ``cell_intg_xy`` / ``col_intg_th`` of every cell / column;
+* ``error_high_resolution`` against a supplied high-resolution solution: the mesh p-refined
+  once in angle and once in space by the reference's ``ref_mesh`` (what
+  ``error_high_resolution.py:46-52`` does for ang_ref_offset = spt_ref_offset = 1), the
+  system on it assembled by the oracle and solved by sparse LU (the reference's own KSP
+  solve needs PETSc), handed to the reference as ``uh_hr``.
 
-Written: ``<case>.amr.npz`` and ``<case>.amr_refined.mesh.json``.
+Written: ``<case>.amr.npz``, ``<case>.amr_refined.mesh.json``, ``<case>.amr_hr.mesh.json``.
 """
 import importlib.abc
 import importlib.util
@@ -30,6 +35,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
 from oracle import ref_harness as H          # noqa: E402
+from oracle import rt_oracle as O            # noqa: E402
 
 FORM = {"": 0, "h": 1, "p": 2}
 REF_TOL = [0.5, 0.5]
@@ -74,7 +80,8 @@ def main():
     from dg.projection import Projection as RefProjection
     import json
     with open(os.path.join(HERE, "SUMMARY.json")) as fh:
-        cases = [k for k in json.load(fh) if not k.startswith("problem:")]
+        summary = json.load(fh)
+    cases = [k for k in summary if not k.startswith("problem:")]
     for case in cases:
         mesh = ref_mesh_from_file(os.path.join(HERE, case + ".mesh.json"))
         u = np.load(os.path.join(HERE, case + ".npz"))["u"]
@@ -104,6 +111,32 @@ def main():
             for kk, _ in sorted(col.cells.items()):
                 ixy.append(np.asarray(proj.cell_intg_xy(ck, kk)).reshape(-1))
         out["intg_xy"], out["intg_th"] = np.concatenate(ixy), np.concatenate(ith)
+        # high-resolution error against a supplied hi-res solution
+        import copy
+        import rt_b200  # noqa: F401
+        from rt_b200 import configs
+        pname = summary[case]["problem"]
+        prob = (configs.manufactured_solution(mesh.Ls)[0] if pname == "manufactured-solution" else
+                configs.one_weak_scatterer(mesh.Ls) if pname == "one-weak-scatterer" else
+                configs.two_strong_scatterers(mesh.Ls))
+        mesh_hr = copy.deepcopy(proj.mesh)
+        mesh_hr.ref_mesh(kind="ang", form="p")
+        mesh_hr.ref_mesh(kind="spt", form="p")
+        ref = O.assemble(mesh_hr, prob.kappa, prob.sigma, prob.Phi)
+        u_hr, _ = O.solve(ref["A"], ref["mask"], O.forcing_vector(mesh_hr, prob.f),
+                          O.bcs_vector(mesh_hr, prob.bcs_dirac[0]), direct=True)
+        uh_hr = RefProjection(mesh_hr)
+        uh_hr.from_vector(u_hr)
+        hr = EI.Error_Indicator(proj, ref_kind="all", ref_form="hp", ref_tol=REF_TOL)
+        hr.error_high_resolution(None, uh_hr=uh_hr)
+        (out["hr_cell_err"], out["hr_cell_ref"], out["hr_cell_form"],
+         out["hr_col_err"], out["hr_col_ref"], out["hr_col_form"]) = flags(hr, proj.mesh)
+        out["hr_scalars"] = np.array([hr.error, hr.error_to_resolve, hr.col_max_error,
+                                      hr.cell_max_error])
+        out["hr_u"] = u_hr
+        mesh_hr.to_file(os.path.join(HERE, case + ".amr_hr.mesh.json"))
+        print(case, "high-resolution error %.6e on %d -> %d DoF" % (hr.error, proj.mesh.get_ndof(),
+                                                                    mesh_hr.get_ndof()))
         out["ref_tol"] = np.array(REF_TOL)
         np.savez_compressed(os.path.join(HERE, case + ".amr.npz"), **out)
         print(case, "angular-jump error %.6e, spatial-jump error %.6e, cells flagged %d / %d, "

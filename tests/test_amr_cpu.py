@@ -190,3 +190,24 @@ def test_spatial_jump_tables_through_kernel_emulation(case):
     u_slab[flat.slab_index_of_dof()] = data["u"]
     e2 = spatial_jump_emulated(flat, tabs, u_slab)
     assert close(np.sqrt(e2), g["sj_col_err"], 1e-10)
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_high_resolution_error_through_kernel_emulation(case):
+    """Interpolation tables + index arithmetic of k_err_hires (tests/emulate.py) against the
+    reference's error_high_resolution on a supplied high-resolution solution."""
+    from emulate import high_resolution_emulated
+    from rt_b200.amr.error_indicator import interpolation_tables
+    mesh, data, _ = load_golden(case)
+    g = amr_golden(case)
+    mesh_hr = mesh_from_file(os.path.join(GOLDEN, case + ".amr_hr.mesh.json"))
+    fl, fh = FlatMesh(mesh), FlatMesh(mesh_hr)
+    ul = np.zeros(fl.n_slab); ul[fl.slab_index_of_dof()] = data["u"]
+    uh = np.zeros(fh.n_slab); uh[fh.slab_index_of_dof()] = g["hr_u"]
+    e2, hr2 = high_resolution_emulated(fl, ul, fh, uh, interpolation_tables())
+    norm2 = hr2.sum()
+    assert close(np.sqrt(e2 / norm2), g["hr_cell_err"], 1e-10)
+    assert close(np.sqrt(e2.sum() / norm2), g["hr_scalars"][0], 1e-10)
+    ncell = [len(col.cells) for _, col in sorted(mesh.cols.items())]
+    col = np.sqrt(np.add.reduceat(e2, np.concatenate([[0], np.cumsum(ncell)[:-1]])) / norm2)
+    assert close(col, g["hr_col_err"], 1e-10)

@@ -144,3 +144,51 @@ def test_spatial_jump_seeded_field_vs_oracle(torch_cuda):
         e2 = AO.spatial_jump(m, u)
         assert close([ei.cols[ck].error for ck in sorted(m.cols)], np.sqrt(e2), 1e-10)
         assert close(ei.error, np.sqrt(e2.sum()), 1e-10)
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_high_resolution_error_matches_reference(case, torch_cuda):
+    """error_high_resolution with the supplied high-resolution solution of the golden file
+    (p-refined mesh, reference-assembled system solved by sparse LU)."""
+    from rt_b200.amr import Error_Indicator
+    from rt_b200.dg.mesh import from_file as mesh_from_file
+    from rt_b200.dg.projection import Projection
+    mesh, d, _ = load_golden(case)
+    g = dict(np.load(os.path.join(GOLDEN, case + ".amr.npz")))
+    mesh_hr = mesh_from_file(os.path.join(GOLDEN, case + ".amr_hr.mesh.json"))
+    uh_hr = Projection(mesh_hr).from_vector(g["hr_u"])
+    ei = Error_Indicator(Projection(mesh).from_vector(d["u"]), ref_kind="all", ref_form="hp",
+                         ref_tol=list(g["ref_tol"]))
+    out = ei.error_high_resolution(None, uh_hr=uh_hr)
+    assert out[0] is uh_hr and out[1] is None and out[2] is None
+    order = [(ck, kk) for ck, col in sorted(mesh.cols.items()) for kk in sorted(col.cells)]
+    assert close([ei.cols[ck].cells[kk].error for ck, kk in order], g["hr_cell_err"], 1e-10)
+    assert close([ei.cols[ck].error for ck in sorted(mesh.cols)], g["hr_col_err"], 1e-10)
+    assert close([ei.error, ei.error_to_resolve, ei.col_max_error, ei.cell_max_error],
+                 g["hr_scalars"], 1e-10)
+    assert np.array_equal([ei.cols[ck].cells[kk].do_ref for ck, kk in order], g["hr_cell_ref"])
+    assert np.array_equal([ei.cols[ck].do_ref for ck in sorted(mesh.cols)], g["hr_col_ref"])
+    assert [ei.cols[ck].cells[kk].ref_form for ck, kk in order] == \
+        [FORM[int(v)] for v in g["hr_cell_form"]]
+
+
+def test_high_resolution_error_runs_its_own_solve(torch_cuda):
+    """Without uh_hr the indicator p-refines the mesh and solves on it through Problem.solve
+    (error_high_resolution.py:46-65): smooth manufactured problem, the estimate must be close
+    to the true discretisation error of the low-resolution solution."""
+    from rt_b200 import configs
+    from rt_b200.amr import Error_Indicator
+    from rt_b200.dg.projection import Projection
+    mesh = configs.build_mesh([3.0, 2.0], [False, False], [3, 3, 3], nref_ang=3, nref_spt=2)
+    prob, u_exact = configs.manufactured_solution(mesh.Ls)
+    uh, conv, _, uvec = prob.solve(mesh, pc_type="none", rtol=1e-11, atol=0.0, max_it=12000,
+                                   return_vector=True)
+    assert conv["converged_reason"] > 0
+    ei = Error_Indicator(uh, ref_kind="all", ref_form="h", ref_tol=[0.5, 0.5])
+    uh_hr, info, minfo = ei.error_high_resolution(prob, ang_ref_offset=1, spt_ref_offset=1,
+                                                  pc_type="none", rtol=1e-11, atol=0.0, max_it=12000)
+    assert info["converged_reason"] > 0
+    assert uh_hr.mesh.get_ndof() > mesh.get_ndof()
+    exact = Projection(mesh, u_exact, vectorized=True).to_vector()
+    true_err = np.linalg.norm(uvec - exact) / np.linalg.norm(exact)
+    assert 0.2 * true_err <= ei.error <= 5.0 * true_err, (ei.error, true_err)
