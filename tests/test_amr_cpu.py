@@ -211,3 +211,93 @@ def test_high_resolution_error_through_kernel_emulation(case):
     ncell = [len(col.cells) for _, col in sorted(mesh.cols.items())]
     col = np.sqrt(np.add.reduceat(e2, np.concatenate([[0], np.cumsum(ncell)[:-1]])) / norm2)
     assert close(col, g["hr_col_err"], 1e-10)
+
+
+# --------------------------------------------------------------------------- #
+# host glue of the three device indicators, with the kernel launches replaced by their
+# numpy emulations / the oracle (the launches themselves are covered by tests/test_gpu_amr.py)
+# --------------------------------------------------------------------------- #
+class _FakeOp:
+    def __init__(self, mesh):
+        self.flat = FlatMesh(mesh)
+        self.n = self.flat.n_dof
+
+    def slab(self, u):
+        out = np.zeros(self.flat.n_slab)
+        out[self.flat.slab_index_of_dof()] = u
+        return out
+
+
+@pytest.fixture
+def emulated_device(monkeypatch):
+    from types import SimpleNamespace
+    from emulate import spatial_jump_emulated, high_resolution_emulated
+    from rt_b200.amr import error_indicator as M
+    from rt_b200.amr.spatial_jump import SpatialJumpTables
+
+    def fake_solution(proj):
+        op = _FakeOp(proj.mesh)
+        return op, (proj.mesh, proj.to_vector(), op.slab(proj.to_vector()))
+
+    def fake_angular(op, u, to_host=True):
+        mesh, vec, _ = u
+        f = op.flat
+        ncell = f.sig_ncell[f.col_sig].astype(np.int64)
+        nt = f.sig_nt[f.col_sig].astype(np.int64)
+        tab = SimpleNamespace(col_cell_off=np.concatenate([[0], np.cumsum(ncell)[:-1]]),
+                              col_th_off=np.concatenate([[0], np.cumsum(nt)[:-1]]))
+        return (AO.angular_jump(mesh, vec), AO.cell_intg_xy(mesh, vec), AO.col_intg_th(mesh, vec), tab)
+
+    def fake_spatial(op, u, to_host=True):
+        return spatial_jump_emulated(op.flat, SpatialJumpTables(op.flat), u[2])
+
+    def fake_hires(op_lo, u_lo, op_hi, u_hi):
+        return high_resolution_emulated(op_lo.flat, u_lo[2], op_hi.flat, u_hi[2],
+                                        M.interpolation_tables())
+
+    monkeypatch.setattr(M, "device_solution", fake_solution)
+    monkeypatch.setattr(M, "device_angular_jump", fake_angular)
+    monkeypatch.setattr(M, "device_spatial_jump", fake_spatial)
+    monkeypatch.setattr(M, "device_high_resolution", fake_hires)
+    return M
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_indicator_host_glue_matches_reference(case, emulated_device):
+    mesh, data, _ = load_golden(case)
+    g = amr_golden(case)
+    proj = Projection(mesh).from_vector(data["u"])
+    order = [(ck, kk) for ck, col in sorted(mesh.cols.items()) for kk in sorted(col.cells)]
+    cols = sorted(mesh.cols)
+
+    ei = Error_Indicator(proj, ref_kind="all", ref_form="hp", ref_tol=list(g["ref_tol"]))
+    ei.error_angular_jump()
+    assert close([ei.cols[ck].cells[kk].error for ck, kk in order], g["aj_cell_err"])
+    assert close([ei.cols[ck].error for ck in cols], g["aj_col_err"])
+    assert close([ei.error, ei.error_to_resolve, ei.col_max_error, ei.cell_max_error], g["aj_scalars"])
+    assert np.array_equal([ei.cols[ck].cells[kk].do_ref for ck, kk in order], g["aj_cell_ref"])
+    assert [ei.cols[ck].cells[kk].ref_form for ck, kk in order] == [FORM[int(v)] for v in g["aj_cell_form"]]
+    assert [ei.cols[ck].ref_form for ck in cols] == [FORM[int(v)] for v in g["aj_col_form"]]
+    assert ei.ref_by_ind() == mesh_from_file(os.path.join(GOLDEN, case + ".amr_refined.mesh.json"))
+
+    ei = Error_Indicator(proj, ref_kind="spt", ref_form="hp", ref_tol=list(g["ref_tol"]))
+    ei.error_spatial_jump()
+    assert close([ei.cols[ck].error for ck in cols], g["sj_col_err"], 1e-10)
+    assert close([ei.error, ei.error_to_resolve, ei.col_max_error], g["sj_scalars"][:3], 1e-10)
+    assert ei.cell_max_error == g["sj_scalars"][3]
+    assert np.array_equal([ei.cols[ck].do_ref for ck in cols], g["sj_col_ref"])
+    assert [ei.cols[ck].ref_form for ck in cols] == [FORM[int(v)] for v in g["sj_col_form"]]
+
+    mesh_hr = mesh_from_file(os.path.join(GOLDEN, case + ".amr_hr.mesh.json"))
+    uh_hr = Projection(mesh_hr).from_vector(g["hr_u"])
+    ei = Error_Indicator(proj, ref_kind="all", ref_form="hp", ref_tol=list(g["ref_tol"]))
+    out = ei.error_high_resolution(None, uh_hr=uh_hr)
+    assert out[0] is uh_hr and out[1] is None
+    assert close([ei.cols[ck].cells[kk].error for ck, kk in order], g["hr_cell_err"], 1e-10)
+    assert close([ei.cols[ck].error for ck in cols], g["hr_col_err"], 1e-10)
+    assert close([ei.error, ei.error_to_resolve, ei.col_max_error, ei.cell_max_error],
+                 g["hr_scalars"], 1e-10)
+    assert np.array_equal([ei.cols[ck].cells[kk].do_ref for ck, kk in order], g["hr_cell_ref"])
+    assert np.array_equal([ei.cols[ck].do_ref for ck in cols], g["hr_col_ref"])
+    assert [ei.cols[ck].cells[kk].ref_form for ck, kk in order] == [FORM[int(v)] for v in g["hr_cell_form"]]
+    assert [ei.cols[ck].ref_form for ck in cols] == [FORM[int(v)] for v in g["hr_col_form"]]
