@@ -192,3 +192,32 @@ def test_high_resolution_error_runs_its_own_solve(torch_cuda):
     exact = Projection(mesh, u_exact, vectorized=True).to_vector()
     true_err = np.linalg.norm(uvec - exact) / np.linalg.norm(exact)
     assert 0.2 * true_err <= ei.error <= 5.0 * true_err, (ei.error, true_err)
+
+
+def test_one_weak_scatterer_hp_amr_cycles(torch_cuda):
+    """experiments/one-weak-scatterer, strategy 'hp-amr-ang' (input.json: ref_kind ang,
+    ref_form hp, ref_tol [0.9, 0]) from a 4 x 4-column start: four cycles of
+    solve (GMRES(50) + node-wise block-Jacobi, which has to cope with the hp angular meshes
+    the loop creates) -> error_angular_jump -> ref_by_ind.  Every cycle: the solution equals
+    the oracle's sparse-LU solution of the reference-assembled system to 1e-8, the mesh
+    sequence is the one the oracle-driven CPU twin of the loop produces."""
+    from rt_b200 import configs
+    from rt_b200.amr import Error_Indicator
+    from oracle import rt_oracle as O, amr_oracle as AO
+    mesh = configs.build_mesh([3.0, 2.0], [False, False], [3, 3, 4], nref_ang=3, nref_spt=2)
+    prob = configs.one_weak_scatterer(mesh.Ls)
+    ndofs = []
+    for cycle in range(4):
+        ndofs.append(mesh.get_ndof())
+        uh, conv, minfo, u = prob.solve(mesh, pc_type="node_bjacobi", rtol=1e-12, atol=0.0,
+                                        max_it=3000, return_vector=True)
+        assert conv["converged_reason"] > 0 and minfo["pc_type_used"] == "node_bjacobi", conv
+        ref = O.assemble(mesh, prob.kappa, prob.sigma, prob.Phi)
+        u_ref, _ = O.solve(ref["A"], ref["mask"], O.forcing_vector(mesh, prob.f),
+                           O.bcs_vector(mesh, prob.bcs_dirac[0]), direct=True)
+        assert np.linalg.norm(u - u_ref) <= 1e-8 * np.linalg.norm(u_ref)
+        ei = Error_Indicator(uh, ref_kind="ang", ref_form="hp", ref_tol=[0.9, 0.0])
+        ei.error_angular_jump()
+        assert close(ei.error, np.sqrt(AO.angular_jump(mesh, u_ref).sum()), 1e-7)
+        mesh = ei.ref_by_ind()
+    assert ndofs == [4608, 4626, 4734, 5472]
