@@ -162,6 +162,7 @@ def device_spatial_jump(op, u_slab, to_host: bool = True):
 
 
 _IP_TABLES = None
+_INTG_U2 = None          # (callable, integral of its square over the domain)
 
 
 def interpolation_tables():
@@ -353,6 +354,39 @@ class Error_Indicator:
         for v in col_hr2:
             intg_uh_hr2 += float(v)
 
+        self._from_cell_err2(cell_err2, intg_uh_hr2)
+        return [uh_hr, info, mat_info]
+
+    def error_analytic(self, anl_sol) -> None:
+        """Relative L2 error against an analytic solution (``error/error_analytic.py:16-190``):
+        the numerical solution interpolated to the nodes of order + 3 in every direction and
+        compared there with ``anl_sol`` (called with broadcastable arrays, as in the
+        reference, ``:103``), normalised by the integral of ``anl_sol^2`` over the domain
+        (``scipy.integrate.nquad``, cached per callable like the reference's global).  Same
+        device kernel as :meth:`error_high_resolution`."""
+        global _INTG_U2
+        if _INTG_U2 is None or _INTG_U2[0] is not anl_sol:
+            from scipy.integrate import nquad
+            [Lx, Ly] = self.proj.mesh.Ls[:]
+            _INTG_U2 = (anl_sol, nquad(lambda x, y, th: (anl_sol(x, y, th)) ** 2,
+                                       [[0, Lx], [0, Ly], [0, 2. * consts.PI]])[0])
+        intg_u2 = _INTG_U2[1]
+        # order + 3 everywhere (error_analytic.py:43,96): set directly -- Mesh.ref_mesh(form="p")
+        # would add more where its degree-balance rule cascades
+        mesh_hr = copy.deepcopy(self.proj.mesh)
+        for col in mesh_hr.cols.values():
+            col.ndofs = [col.ndofs[0] + 3, col.ndofs[1] + 3]
+            for cell in col.cells.values():
+                cell.ndofs = [cell.ndofs[0] + 3]
+        u_hr = Projection(mesh_hr, anl_sol, vectorized=True)
+        op_hi, u_hi = device_solution(u_hr)
+        op_lo, u_lo = self._device_solution()
+        cell_err2, _ = device_high_resolution(op_lo, u_lo, op_hi, u_hi)
+        self._from_cell_err2(cell_err2, intg_u2)
+
+    def _from_cell_err2(self, cell_err2, norm2) -> None:
+        """cols / maxima / flags from per-cell squared errors and the squared norm they are
+        relative to (``error_high_resolution.py:116-216``, ``error_analytic.py:30-145``)."""
         cols: dict = {}
         col_max_err = -consts.INF
         cell_max_err = -consts.INF
@@ -368,18 +402,17 @@ class Error_Indicator:
                 k += 1
                 col_err += e2
                 mesh_err += e2
-                err = float(np.sqrt(e2 / intg_uh_hr2))
+                err = float(np.sqrt(e2 / norm2))
                 cells[cell_key] = Error_Indicator_Cell(err)
                 cell_max_err = max(cell_max_err, err)
-            cols[col_key] = Error_Indicator_Column(float(np.sqrt(col_err / intg_uh_hr2)), cells)
+            cols[col_key] = Error_Indicator_Column(float(np.sqrt(col_err / norm2)), cells)
             col_max_err = max(col_max_err, cols[col_key].error)
         self.cols = cols
         self.col_max_error = col_max_err
         self.cell_max_error = cell_max_err
-        self.error = float(np.sqrt(mesh_err / intg_uh_hr2))
+        self.error = float(np.sqrt(mesh_err / norm2))
         self._intg_xy = self._intg_th = None       # hp steering from the projection's values
         self._mark()
-        return [uh_hr, info, mat_info]
 
     def error_random(self, rng=None) -> None:
         """Uniform random indicator per cell (``error/error_random.py:15-91``)."""

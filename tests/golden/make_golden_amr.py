@@ -137,6 +137,16 @@ def main():
         mesh_hr.to_file(os.path.join(HERE, case + ".amr_hr.mesh.json"))
         print(case, "high-resolution error %.6e on %d -> %d DoF" % (hr.error, proj.mesh.get_ndof(),
                                                                     mesh_hr.get_ndof()))
+        if pname == "manufactured-solution":
+            # error against the analytic solution (error_analytic.py; nquad of u^2 inside)
+            u_exact = configs.manufactured_solution(mesh.Ls)[1]
+            an = EI.Error_Indicator(proj, ref_kind="all", ref_form="hp", ref_tol=REF_TOL)
+            an.error_analytic(u_exact)
+            (out["an_cell_err"], out["an_cell_ref"], out["an_cell_form"],
+             out["an_col_err"], out["an_col_ref"], out["an_col_form"]) = flags(an, proj.mesh)
+            out["an_scalars"] = np.array([an.error, an.error_to_resolve, an.col_max_error,
+                                          an.cell_max_error])
+            print(case, "analytic error %.6e" % an.error)
         out["ref_tol"] = np.array(REF_TOL)
         np.savez_compressed(os.path.join(HERE, case + ".amr.npz"), **out)
         print(case, "angular-jump error %.6e, spatial-jump error %.6e, cells flagged %d / %d, "

@@ -301,3 +301,23 @@ def test_indicator_host_glue_matches_reference(case, emulated_device):
     assert np.array_equal([ei.cols[ck].do_ref for ck in cols], g["hr_col_ref"])
     assert [ei.cols[ck].cells[kk].ref_form for ck, kk in order] == [FORM[int(v)] for v in g["hr_cell_form"]]
     assert [ei.cols[ck].ref_form for ck in cols] == [FORM[int(v)] for v in g["hr_col_form"]]
+
+
+@pytest.mark.parametrize("case", ["c1_manufactured", "hp_manufactured"])
+def test_error_analytic_host_glue_matches_reference(case, emulated_device):
+    from rt_b200 import configs
+    mesh, data, _ = load_golden(case)
+    g = amr_golden(case)
+    u_exact = configs.manufactured_solution(mesh.Ls)[1]
+    ei = Error_Indicator(Projection(mesh).from_vector(data["u"]), ref_kind="all", ref_form="hp",
+                         ref_tol=list(g["ref_tol"]))
+    ei.error_analytic(u_exact)
+    order = [(ck, kk) for ck, col in sorted(mesh.cols.items()) for kk in sorted(col.cells)]
+    cols = sorted(mesh.cols)
+    assert close([ei.cols[ck].cells[kk].error for ck, kk in order], g["an_cell_err"], 1e-10)
+    assert close([ei.cols[ck].error for ck in cols], g["an_col_err"], 1e-10)
+    assert close([ei.error, ei.error_to_resolve, ei.col_max_error, ei.cell_max_error],
+                 g["an_scalars"], 1e-10)
+    assert np.array_equal([ei.cols[ck].cells[kk].do_ref for ck, kk in order], g["an_cell_ref"])
+    assert np.array_equal([ei.cols[ck].do_ref for ck in cols], g["an_col_ref"])
+    assert [ei.cols[ck].cells[kk].ref_form for ck, kk in order] == [FORM[int(v)] for v in g["an_cell_form"]]

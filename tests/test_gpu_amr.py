@@ -221,3 +221,22 @@ def test_one_weak_scatterer_hp_amr_cycles(torch_cuda):
         assert close(ei.error, np.sqrt(AO.angular_jump(mesh, u_ref).sum()), 1e-7)
         mesh = ei.ref_by_ind()
     assert ndofs == [4608, 4626, 4734, 5472]
+
+
+@pytest.mark.parametrize("case", ["c1_manufactured", "hp_manufactured"])
+def test_error_analytic_matches_reference(case, torch_cuda):
+    from rt_b200 import configs
+    from rt_b200.amr import Error_Indicator
+    from rt_b200.dg.projection import Projection
+    mesh, d, _ = load_golden(case)
+    g = dict(np.load(os.path.join(GOLDEN, case + ".amr.npz")))
+    u_exact = configs.manufactured_solution(mesh.Ls)[1]
+    ei = Error_Indicator(Projection(mesh).from_vector(d["u"]), ref_kind="all", ref_form="hp",
+                         ref_tol=list(g["ref_tol"]))
+    ei.error_analytic(u_exact)
+    order = [(ck, kk) for ck, col in sorted(mesh.cols.items()) for kk in sorted(col.cells)]
+    assert close([ei.cols[ck].cells[kk].error for ck, kk in order], g["an_cell_err"], 1e-10)
+    assert close([ei.cols[ck].error for ck in sorted(mesh.cols)], g["an_col_err"], 1e-10)
+    assert close([ei.error, ei.error_to_resolve, ei.col_max_error, ei.cell_max_error],
+                 g["an_scalars"], 1e-10)
+    assert np.array_equal([ei.cols[ck].cells[kk].do_ref for ck, kk in order], g["an_cell_ref"])
