@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define RTB200_ABI_VERSION 4
+#define RTB200_ABI_VERSION 5
 
 /* error codes */
 #define RTB200_OK            0
@@ -281,6 +281,8 @@ int  rtb200_halo_exchange(rtb200_ctx* ctx, const double* x_slab_dev, void* strea
  *        col_cell_off [n_col]  first entry of column c in cell_err2
  *        col_th_off   [n_col]  first entry of column c in cell_intg_xy
  *        max_cell_nodes        max over columns of (cells x spatial nodes)
+ *        max_slab_doubles      max over columns of nx * ny * row stride (the slab is staged
+ *                              in shared memory when it fits); 0: never stage
  *      Outputs (device):
  *        cell_err2    [sum of cells]    squared cell indicator, cells in sorted-key order
  *        cell_intg_xy [sum of n_theta]  (dx dy/4) sum_ij w_i w_j u, theta in slab order
@@ -291,8 +293,8 @@ int  rtb200_err_angular_jump(rtb200_ctx* ctx, const double* u_slab_dev,
                              const double* lag_bot_dev, const double* lag_top_dev,
                              const double* lgl_w_dev, const int64_t* col_cell_off_dev,
                              const int64_t* col_th_off_dev, int32_t max_cell_nodes,
-                             double* cell_err2_dev, double* cell_intg_xy_dev,
-                             double* col_intg_th_dev, void* stream);
+                             int32_t max_slab_doubles, double* cell_err2_dev,
+                             double* cell_intg_xy_dev, double* col_intg_th_dev, void* stream);
 
 /* ---- spatial-jump indicator (replaces src/amr/Error_Indicator/error/
  *      error_spatial_jump.py:30-252): per column, the squared difference of the two
@@ -303,9 +305,10 @@ int  rtb200_err_angular_jump(rtb200_ctx* ctx, const double* u_slab_dev,
  *        sp_off / ap_off / nb [n_col*8]  per (column, face, slot): offset of the spatial
  *                  block [S0: n0 x nB][S1: n1 x nB][wB: nB][dA] in pool (-1: no
  *                  neighbour), offset of the (signature, neighbour signature) table in
- *                  apair, nB
+ *                  apair, nB (negative: S0 = S1 = identity, same nodes on both sides)
  *        apair     [ncell0][2][4] per signature pair: (angular block offset in pool | -1,
- *                  first theta of the neighbour cell, nth1, nH); angular block =
+ *                  first theta of the neighbour cell, nth1, nH (negative: T0 = T1 =
+ *                  identity)); angular block =
  *                  [T0: nth0 x nH][T1: nth1 x nH][wH: nH][dG]
  *      Output: col_err2 [n_col] (device) ------------------------------------ */
 int  rtb200_err_spatial_jump(rtb200_ctx* ctx, const double* u_slab_dev,

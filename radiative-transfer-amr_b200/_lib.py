@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_NXY = 12
 MAX_NTH = 16
 
@@ -90,7 +90,7 @@ SYMBOLS = {
     "rtb200_pc_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rtb200_pc_set_shift": (C.c_int, [C.c_void_p, C.c_double]),
     "rtb200_pc_set_eig": (C.c_int, [C.c_void_p, _i64p, C.c_int32, _f64p, C.c_int64]),
-    "rtb200_err_angular_jump": (C.c_int, [C.c_void_p] + [C.c_void_p] * 8 + [C.c_int32]
+    "rtb200_err_angular_jump": (C.c_int, [C.c_void_p] + [C.c_void_p] * 8 + [C.c_int32] * 2
                                 + [C.c_void_p] * 4),
     "rtb200_err_spatial_jump": (C.c_int, [C.c_void_p] * 9),
     "rtb200_err_high_resolution": (C.c_int, [C.c_void_p] * 11 + [C.c_int32] + [C.c_void_p] * 3),

@@ -103,6 +103,7 @@ class IndicatorTables:
         self.n_cells, self.n_theta = int(ncell.sum()), int(nt.sum())
         self.n_nodes = int(nn.sum())
         self.max_cell_nodes = int((ncell * nn).max()) if ncell.size else 1
+        self.max_slab_doubles = int((nn * f.sig_ntp[f.col_sig]).max()) if ncell.size else 0
 
         def dev(a, dt):
             return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(op.device)
@@ -131,7 +132,8 @@ def device_angular_jump(op, u_slab, to_host: bool = True):
     op._call("rtb200_err_angular_jump", op.lib.rtb200_err_angular_jump(
         op.ctx, p(u_slab), p(tab.cell_lo), p(tab.cell_up), p(tab.lag_bot), p(tab.lag_top),
         p(tab.lgl_w), p(tab.col_cell_off_dev), p(tab.col_th_off_dev),
-        C.c_int32(tab.max_cell_nodes), p(err2), p(ixy), p(ith), op._stream()))
+        C.c_int32(tab.max_cell_nodes), C.c_int32(tab.max_slab_doubles), p(err2), p(ixy), p(ith),
+        op._stream()))
     if not to_host:
         return err2, ixy, ith, tab
     return (err2[:tab.n_cells].cpu().numpy(), ixy[:tab.n_theta].cpu().numpy(),

@@ -16,6 +16,9 @@ two intervals), so they are pooled and shared:
 * per (column, face, slot): spatial block offset and the offset of the
   (signature, neighbour signature) pair table ``[ncell0][2][4] = (angular block
   offset | -1, first theta of the neighbour cell, nth1, nH)``.
+
+A NEGATIVE nB / nH marks identity tables (both sides have the same nodes: conforming face,
+same angular cell): the kernel then takes the nodal difference directly.
 """
 from __future__ import annotations
 
@@ -87,7 +90,9 @@ class SpatialJumpTables:
                     key = ("s", n0, n1, _rel(a0, b0, a1, b1), float(min(b0 - a0, b1 - a1)))
                     self.sp_off[fidx] = pool.block(
                         key, lambda: interp_pair(a0, b0, n0, a1, b1, n1, lgl_rule))
-                    self.nb[fidx] = max(n0, n1)
+                    # same nodes on both sides: S0 = S1 = identity (the kernel's nodal fast path)
+                    same = n0 == n1 and _rel(a0, b0, a1, b1) == (0.0, 1.0)
+                    self.nb[fidx] = -n0 if same else max(n0, n1)
                     s0, s1 = int(A.sig[c]), int(A.sig[d])
                     if (s0, s1) not in pair_ids:
                         sg0, sg1 = A.sigs[s0], A.sigs[s1]
@@ -101,7 +106,9 @@ class SpatialJumpTables:
                                         float(min(t0b - t0a, t1b - t1a)))
                                 off = pool.block(akey, lambda: interp_pair(
                                     t0a, t0b, m0, t1a, t1b, m1, lg_rule))
-                                tab[k0, k] = (off, int(sg1.thoff[k1]), m1, max(m0, m1))
+                                same_a = m0 == m1 and _rel(t0a, t0b, t1a, t1b) == (0.0, 1.0)
+                                tab[k0, k] = (off, int(sg1.thoff[k1]), m1,
+                                              -m0 if same_a else max(m0, m1))
                         pair_ids[(s0, s1)] = n_pair
                         pair_parts.append(tab.reshape(-1))
                         n_pair += tab.size
@@ -110,4 +117,4 @@ class SpatialJumpTables:
         self.apair = np.concatenate(pair_parts).astype(np.int32) if pair_parts \
             else np.zeros(4, np.int32)
         assert self.pool.size < 2 ** 31 and self.apair.size < 2 ** 31
-        assert int(self.nb.max(initial=0)) <= L.MAX_NXY
+        assert int(np.abs(self.nb).max(initial=0)) <= L.MAX_NXY

@@ -36,7 +36,7 @@ k_err_angular(DevMesh m, const double* __restrict__ u, const int32_t* __restrict
               const double* __restrict__ lag_top, const double* __restrict__ lgl_w,
               const int64_t* __restrict__ col_cell_off, const int64_t* __restrict__ col_th_off,
               double* __restrict__ cell_err2, double* __restrict__ intg_xy,
-              double* __restrict__ intg_th) {
+              double* __restrict__ intg_th, const int trace_doubles, const int stage) {
     extern __shared__ __align__(16) double ei_s[];
     const int c = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -46,27 +46,37 @@ k_err_angular(DevMesh m, const double* __restrict__ u, const int32_t* __restrict
     const int nt = m.sig_nt[sg], ntp = m.sig_ntp[sg];
     const int64_t tp0 = m.sig_th0[sg];
     const int cell0 = m.sig_cell0[sg], ncell = m.sig_ncell[sg];
-    const double* __restrict__ uc = u + m.col_slab_off[c];
+    const double* uc = u + m.col_slab_off[c];
     const double* __restrict__ wx = lgl_w + nx * RT_MAXN;
     const double* __restrict__ wy = lgl_w + ny * RT_MAXN;
     double* const tops = ei_s;                       // [ncell][nn]
     double* const bots = ei_s + (size_t)ncell * nn;  // [ncell][nn]
+    if (stage) {
+        // the column's slab, read from HBM once with coalesced loads; the three reductions
+        // below then run from shared memory (host: every column fits, else stage = 0)
+        double* const us = ei_s + 2 * (size_t)trace_doubles;
+        const int tot = nn * ntp;
+        for (int e = tid; e < tot; e += EI_THREADS) us[e] = uc[e];
+        __syncthreads();
+        uc = us;
+    }
 
     // ---- traces at the upper / lower end of every cell (error_angular_jump.py:31-51) ---- //
+    // (cell index fastest: neighbouring threads read neighbouring chunks of one row)
     for (int e = tid; e < ncell * nn; e += EI_THREADS) {
-        const int K = e / nn, n = e - K * nn;
+        const int n = e / ncell, K = e - n * ncell;
         const int nth = m.cell_nth[cell0 + K], tho = m.cell_thoff[cell0 + K];
         const double* __restrict__ lb = lag_bot + nth * RTB200_MAX_NTH;
         const double* __restrict__ lt = lag_top + nth * RTB200_MAX_NTH;
-        const double* __restrict__ row = uc + (int64_t)n * ntp + tho;
+        const double* row = uc + (int64_t)n * ntp + tho;
         double t = 0.0, b = 0.0;
         for (int a = 0; a < nth; ++a) {
             const double v = row[a];
             t = fma(v, lt[a], t);
             b = fma(v, lb[a], b);
         }
-        tops[e] = t;
-        bots[e] = b;
+        tops[K * nn + n] = t;
+        bots[K * nn + n] = b;
     }
     __syncthreads();
 
@@ -98,7 +108,7 @@ k_err_angular(DevMesh m, const double* __restrict__ u, const int32_t* __restrict
     // ---- angular integral per node (col_intg_th.py:22-41): warp per node ----------------- //
     const int64_t n0 = m.col_coef_off[c] >> 1;
     for (int n = warp; n < nn; n += NW) {
-        const double* __restrict__ row = uc + (int64_t)n * ntp;
+        const double* row = uc + (int64_t)n * ntp;
         double s = 0.0;
         for (int th = lane; th < nt; th += 32) s = fma(m.th_wt[tp0 + th], row[th], s);
         s = warp_sum(s);
@@ -140,9 +150,13 @@ k_err_spatial(DevMesh m, const double* __restrict__ u, const int32_t* __restrict
         const int32_t* __restrict__ ap = apair + ap_off[fidx] + (K0 * 2 + k) * 4;
         const int ao = ap[0];
         if (ao < 0) continue;
-        const int tho1 = ap[1], nth1 = ap[2], nH = ap[3];
+        const int tho1 = ap[1], nth1 = ap[2];
         const int nth0 = m.cell_nth[cell0 + K0], tho0 = m.cell_thoff[cell0 + K0];
-        const int n0 = (F & 1) ? nx : ny, n1 = m.face_n1[fidx], nB = nb_tab[fidx];
+        const int n0 = (F & 1) ? nx : ny, n1 = m.face_n1[fidx];
+        // a negative count marks identity tables (same nodes on both sides)
+        const int nBs = nb_tab[fidx], nHs = ap[3];
+        const int nB = nBs < 0 ? -nBs : nBs, nH = nHs < 0 ? -nHs : nHs;
+        const bool conforming = nBs < 0 && nHs < 0;
         const int rs1 = m.face_rstride[fidx];
         // own face rows: F = 0: i = nx-1; 1: j = ny-1; 2: i = 0; 3: j = 0
         const int node0 = F == 0 ? (nx - 1) * ny : (F == 1 ? ny - 1 : 0);
@@ -158,6 +172,15 @@ k_err_spatial(DevMesh m, const double* __restrict__ u, const int32_t* __restrict
         const double* __restrict__ u0 = uc + (int64_t)node0 * ntp + tho0;
         const double* __restrict__ u1 = u + base1 + tho1;
         double s = 0.0;
+        if (conforming) {           // warp-uniform: the jump is the nodal difference
+            for (int e = lane; e < nB * nH; e += 32) {
+                const int p = e / nH, q = e - p * nH;
+                const double d = u0[(int64_t)p * step0 * ntp + q] - u1[(int64_t)p * rs1 + q];
+                s = fma(wB[p] * wH[q], d * d, s);
+            }
+            acc = fma(0.25 * dA * dG, s, acc);
+            continue;
+        }
         for (int e = lane; e < nB * nH; e += 32) {
             const int p = e / nH, q = e - p * nH;
             double d = 0.0;
@@ -335,25 +358,32 @@ extern "C" int rtb200_err_angular_jump(rtb200_ctx* ctx, const double* u_slab_dev
                                        const double* lag_bot_dev, const double* lag_top_dev,
                                        const double* lgl_w_dev, const int64_t* col_cell_off_dev,
                                        const int64_t* col_th_off_dev, int32_t max_cell_nodes,
-                                       double* cell_err2_dev, double* cell_intg_xy_dev,
-                                       double* col_intg_th_dev, void* stream) {
+                                       int32_t max_slab_doubles, double* cell_err2_dev,
+                                       double* cell_intg_xy_dev, double* col_intg_th_dev,
+                                       void* stream) {
     if (!ctx) return RTB200_EINVAL;
     if (!ctx->have_mesh) return rt_fail(ctx, RTB200_ESTATE, "rtb200_err_angular_jump: no mesh set");
     if (!u_slab_dev || !cell_lo_dev || !cell_up_dev || !lag_bot_dev || !lag_top_dev || !lgl_w_dev ||
         !col_cell_off_dev || !col_th_off_dev || !cell_err2_dev || !cell_intg_xy_dev || !col_intg_th_dev)
         return rt_fail(ctx, RTB200_EINVAL, "rtb200_err_angular_jump: null pointer");
     if (max_cell_nodes <= 0) return rt_fail(ctx, RTB200_EINVAL, "rtb200_err_angular_jump: max_cell_nodes <= 0");
-    const size_t smem = 2 * sizeof(double) * (size_t)max_cell_nodes;
+    size_t smem = 2 * sizeof(double) * (size_t)max_cell_nodes;
     if (smem > 200 * 1024)
         return rt_fail(ctx, RTB200_EUNSUPPORTED,
                        "rtb200_err_angular_jump: a column with more than 12800 (cell, node) pairs");
+    // stage the slab in shared memory when every column fits next to its traces and at
+    // least two blocks stay resident per SM
+    const int stage = max_slab_doubles > 0 &&
+                      smem + sizeof(double) * (size_t)max_slab_doubles <= 100 * 1024;
+    if (stage) smem += sizeof(double) * (size_t)max_slab_doubles;
     if (ctx->dm.n_col == 0) return RTB200_OK;
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
     if (smem > 48 * 1024)
         RT_CUDA(ctx, cudaFuncSetAttribute(k_err_angular, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_err_angular<<<ctx->dm.n_col, EI_THREADS, smem, (cudaStream_t)stream>>>(
         ctx->dm, u_slab_dev, cell_lo_dev, cell_up_dev, lag_bot_dev, lag_top_dev, lgl_w_dev,
-        col_cell_off_dev, col_th_off_dev, cell_err2_dev, cell_intg_xy_dev, col_intg_th_dev);
+        col_cell_off_dev, col_th_off_dev, cell_err2_dev, cell_intg_xy_dev, col_intg_th_dev,
+        (int)max_cell_nodes, stage);
     ctx->launches++;
     RT_CUDA(ctx, cudaGetLastError());
     return RTB200_OK;

@@ -142,10 +142,11 @@ def spatial_jump_emulated(flat, tabs, u_slab):
             ao = int(ap[0])
             if ao < 0:
                 continue
-            tho1, nth1, nH = int(ap[1]), int(ap[2]), int(ap[3])
+            tho1, nth1, nHs = int(ap[1]), int(ap[2]), int(ap[3])
             nth0, tho0 = int(flat.cell_nth[cell0 + K0]), int(flat.cell_thoff[cell0 + K0])
             n0 = nx if (F & 1) else ny
-            n1, nB = int(flat.face_n1[fidx]), int(tabs.nb[fidx])
+            n1, nBs = int(flat.face_n1[fidx]), int(tabs.nb[fidx])
+            nB, nH = abs(nBs), abs(nHs)
             rs1 = int(flat.face_rstride[fidx])
             node0 = (nx - 1) * ny if F == 0 else (ny - 1 if F == 1 else 0)
             step0 = ny if (F & 1) else 1
@@ -160,7 +161,12 @@ def spatial_jump_emulated(flat, tabs, u_slab):
             dG = P[ao + (nth0 + nth1) * nH + nH]
             u0 = np.stack([u_slab[soff + (node0 + j * step0) * ntp + tho0:][:nth0] for j in range(n0)])
             u1 = np.stack([u_slab[base1 + j * rs1 + tho1:][:nth1] for j in range(n1)])
-            d = S0.T @ u0 @ T0 - S1.T @ u1 @ T1
+            if nBs < 0 and nHs < 0:          # the kernel's conforming fast path
+                for tab_, n_ in ((S0, nB), (S1, nB), (T0, nH), (T1, nH)):   # identity up to rounding
+                    assert np.allclose(tab_, np.eye(n_), rtol=0.0, atol=1e-13)
+                d = u0 - u1
+            else:
+                d = S0.T @ u0 @ T0 - S1.T @ u1 @ T1
             acc += 0.25 * dA * dG * np.sum(wB[:, None] * wH[None, :] * d * d)
         perim = 2.0 * flat.col_dx[c] + 2.0 * flat.col_dy[c]
         out[c] = acc / (perim * 2.0 * np.pi)
