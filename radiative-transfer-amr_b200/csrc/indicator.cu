@@ -54,9 +54,15 @@ k_err_angular(DevMesh m, const double* __restrict__ u, const int32_t* __restrict
     if (stage) {
         // the column's slab, read from HBM once with coalesced loads; the three reductions
         // below then run from shared memory (host: every column fits, else stage = 0)
+        // (16-byte asynchronous copies, all in flight at once: one memory latency per column;
+        // slab offsets and row strides are even, so every chunk is 16-byte aligned)
         double* const us = ei_s + 2 * (size_t)trace_doubles;
-        const int tot = nn * ntp;
-        for (int e = tid; e < tot; e += EI_THREADS) us[e] = uc[e];
+        const int chunks = (nn * ntp) >> 1;
+        for (int e = tid; e < chunks; e += EI_THREADS) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(us + 2 * e);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(uc + 2 * e));
+        }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
         __syncthreads();
         uc = us;
     }
