@@ -79,7 +79,9 @@ struct GroupTab {
 
 // TH threads per block: 256, or 128 for buckets of short rows (<= 64 angles: few n-tiles
 // and few (column, angle) items, so half the warps of a 256-thread block would idle)
-template <int N, int TH>
+// NODE: streaming phase with one thread per (column, node, angle) instead of one per
+// (column, angle) -- RTB200_HP_STREAM=node in the environment (see stream_node_theta)
+template <int N, int TH, bool NODE = false>
 __global__ void __launch_bounds__(TH, 512 / TH)
 k_apply(DevMesh m, GroupTab gt, unsigned terms, int interior_only, const double* __restrict__ x,
         const double* __restrict__ ghost, double* __restrict__ y, int ntps) {
@@ -121,7 +123,21 @@ k_apply(DevMesh m, GroupTab gt, unsigned terms, int interior_only, const double*
     __syncthreads();
 
     // ---- phase 1: streaming terms, one thread per (column, theta) ------------ //
-    if (terms & (RTB200_TERM_MASS | RTB200_TERM_ICONV | RTB200_TERM_BCONV)) {
+    if (NODE && (terms & (RTB200_TERM_MASS | RTB200_TERM_ICONV | RTB200_TERM_BCONV))) {
+        const int per_col = nn * ntp;
+        for (int item = threadIdx.x; item < cg_n * per_col; item += TH) {
+            const int cg = item / per_col, rem = item - cg * per_col;
+            const int n = rem / ntp, th = rem - n * ntp;       // angle fastest: coalesced stores
+            const int c = s_col[cg];
+            if (th >= nt) {
+                y[m.col_slab_off[c] + (int64_t)n * ntp + th] = 0.0;
+                continue;
+            }
+            const int i = n / ny;
+            stream_node_theta<N>(m, c, th, i, n - i * ny, nx, ny, sg, ntp, tp0, u_s + cg * nn * ntps, ntps,
+                                 terms, interior_only, x, ghost, y);
+        }
+    } else if (terms & (RTB200_TERM_MASS | RTB200_TERM_ICONV | RTB200_TERM_BCONV)) {
         for (int item = threadIdx.x; item < cg_n * ntp; item += TH) {
             const int cg = item / ntp, th = item - cg * ntp;
             const int c = s_col[cg];
@@ -312,7 +328,8 @@ template <int N>
 static int launch_bucket(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int interior_only,
                          const double* x, double* y, cudaStream_t st) {
     const bool small = b.max_ntp <= 64;
-    auto kern = small ? k_apply<N, 128> : k_apply<N, 256>;
+    auto kern = ctx->hp_node_stream ? (small ? k_apply<N, 128, true> : k_apply<N, 256, true>)
+                                    : (small ? k_apply<N, 128, false> : k_apply<N, 256, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.smem);
     if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaFuncSetAttribute(k_apply, smem)");
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,

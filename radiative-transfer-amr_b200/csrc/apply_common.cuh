@@ -167,3 +167,99 @@ __device__ __forceinline__ void stream_column_theta(
         }
     }
 }
+
+
+// Same terms for ONE node (i, j) of column c at angular index th (< nt): the item of the
+// node-parallel streaming phase (k_apply<N, TH, true>).  A (column, angle) pair is spread
+// over nx * ny threads instead of one, so a group of a few small hp columns fills the
+// block; the price is that the threads of a mortar face each recompute the neighbour's
+// angular-mortared trace values they need (the tables are L1-resident).  Operation order
+// per output entry is the one of stream_column_theta: results are bit-identical.
+template <int N>
+__device__ __forceinline__ void stream_node_theta(
+    const DevMesh& m, const int c, const int th, const int i, const int j, const int nx, const int ny,
+    const int sg, const int ntp, const int64_t tp0, const double* __restrict__ us, const int ustride,
+    const unsigned terms, const int interior_only, const double* __restrict__ x,
+    const double* __restrict__ ghost, double* __restrict__ y) {
+    constexpr int NF = N > 0 ? N : RT_MAXN;
+    const double* wx = c_w + nx * RT_MAXN;
+    const double* wy = c_w + ny * RT_MAXN;
+    const double* Sx = c_s + nx * RT_MAXN * RT_MAXN;
+    const double* Sy = c_s + ny * RT_MAXN * RT_MAXN;
+    const int n = i * ny + j;
+    const double hdx = 0.5 * m.col_dx[c], hdy = 0.5 * m.col_dy[c];
+    const int bdry = m.col_bdry[c];
+    const double* __restrict__ mk = m.coef + m.col_coef_off[c];
+    const int bits = m.th_bits[tp0 + th];
+    const double u0 = us[n * ustride + th];
+    double v = 0.0;
+    if (terms & RTB200_TERM_MASS) v = mk[n] * m.th_wt[tp0 + th] * u0;
+    if (terms & RTB200_TERM_ICONV) {
+        const double ct = m.th_ct[tp0 + th], st = m.th_st[tp0 + th];
+        double sx = 0.0, sy = 0.0;
+#pragma unroll
+        for (int k = 0; k < NF; ++k)
+            if (k < nx) sx = fma(Sx[i * RT_MAXN + k], us[(k * ny + j) * ustride + th], sx);
+#pragma unroll
+        for (int k = 0; k < NF; ++k)
+            if (k < ny) sy = fma(Sy[j * RT_MAXN + k], us[(i * ny + k) * ustride + th], sy);
+        v -= hdy * wy[j] * ct * sx + hdx * wx[i] * st * sy;
+    }
+    if (terms & RTB200_TERM_BCONV) {
+        const bool on_face[4] = {i == nx - 1, j == ny - 1, i == 0, j == 0};
+#pragma unroll
+        for (int F = 0; F < 4; ++F) {
+            if (!on_face[F]) continue;
+            const int q = (F & 1) ? i : j;               // position along the face
+            const double half = (F & 1) ? hdx : hdy;
+            const double* wq = (F & 1) ? wx : wy;
+            const double wF = m.th_wF[F * m.n_theta_pool + tp0 + th];
+            if ((bits >> F) & 1) {                       // outflow: own trace
+                v += half * wq[q] * wF * u0;
+                continue;
+            }
+            if ((bdry >> F) & 1) continue;               // inflow through the domain boundary
+            const int n0 = (F & 1) ? nx : ny;
+            const int cell = m.th_cell[tp0 + th];
+            const int r = (bits >> 8) & 0xff;
+            const int nth0 = m.cell_nth[m.sig_cell0[sg] + cell];
+            double fa = 0.0;
+            for (int slot = 0; slot < 2; ++slot) {
+                const int fidx = c * 8 + F * 2 + slot;
+                const int64_t base = m.face_base[fidx];
+                if (base == -1) continue;
+                const double* __restrict__ src = base >= 0 ? x + base : ghost + (-(base + 2));
+                const int rs = m.face_rstride[fidx];
+                const int eo = m.face_exy[fidx];
+                const int ao = m.face_acpl[fidx];
+                if (eo < 0 && ao < 0) {                  // conforming neighbour
+                    fa = (half * wF) * wq[q] * src[(int64_t)q * rs + th];
+                    continue;
+                }
+                const int n1 = m.face_n1[fidx];
+                for (int j1 = 0; j1 < n1; ++j1) {
+                    if (eo < 0 && j1 != q) continue;     // E = diag(w): one term
+                    double tmp;
+                    if (ao < 0) {
+                        tmp = wF * src[(int64_t)j1 * rs + th];
+                    } else {
+                        const int32_t* __restrict__ acp = m.acpl_pool + ao + cell * 6;
+                        tmp = 0.0;
+                        for (int k = 0; k < 2; ++k) {
+                            const int n1t = acp[k * 3 + 2];
+                            if (n1t == 0) continue;
+                            const double* __restrict__ eth = m.eth_pool + acp[k * 3] + r;
+                            const double* __restrict__ tr = src + (int64_t)j1 * rs + acp[k * 3 + 1];
+                            for (int a = 0; a < n1t; ++a) tmp = fma(eth[a * nth0], tr[a], tmp);
+                        }
+                    }
+                    tmp *= half;
+                    fa = fma(eo < 0 ? wq[q] : m.exy_pool[eo + j1 * n0 + q], tmp, fa);
+                }
+            }
+            v += fa;
+        }
+    }
+    const bool masked = interior_only && dof_masked(i, j, nx, ny, bdry, bits);
+    y[m.col_slab_off[c] + th + (int64_t)n * ntp] = masked ? 0.0 : v;
+}

@@ -76,6 +76,7 @@ struct rtb200_ctx {
     const double* circ_pool_dev = nullptr;
     bool use_circ = true;          // RTB200_DENSE_SCATTERING=1 in the environment disables it
     int circ_version = 7;          // RTB200_CIRC_VERSION=6 selects the one-block-per-column kernel
+    bool hp_node_stream = false;   // RTB200_HP_STREAM=node: node-parallel streaming phase of k_apply
     int64_t launches = 0;
     int sm_count = 148;
 

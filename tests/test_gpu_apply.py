@@ -135,3 +135,26 @@ def test_seeded_hp_synthetic_mesh_matches_oracle(level):
     yi = op.mult(x * mask, interior_only=True)
     assert rel_err(yi[mask], (ref["A"] @ (x * mask))[mask]) <= 1e-11
     assert np.all(yi[~mask] == 0.0)
+
+
+@pytest.mark.parametrize("case", ["hp_mixed", "test_mesh_script", "periodic_small", "c1_uniform"])
+def test_node_parallel_streaming_equals_column_streaming(case, monkeypatch):
+    """RTB200_HP_STREAM=node (one thread per (column, node, angle) in the streaming phase of
+    k_apply) against the default (one thread per (column, angle)): same operation order per
+    entry, results equal to rounding; dense path forced so that every column takes k_apply."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    from rt_b200.rt import RTOperator
+    mesh, d, prob = load_golden(case)
+    monkeypatch.setenv("RTB200_DENSE_SCATTERING", "1")
+    outs = {}
+    for mode in ("column", "node"):
+        monkeypatch.setenv("RTB200_HP_STREAM", mode)
+        op = RTOperator(mesh, prob.kappa, prob.sigma, prob.Phi)
+        outs[mode] = {(t, io): op.mult(d["x"], None, t, io)
+                      for t, io in ((15, False), (15, True), (8, False), (5, False))}
+        op.close()
+    for key, ref in outs["column"].items():
+        assert rel_err(outs["node"][key], ref) <= 1e-13, (key, rel_err(outs["node"][key], ref))
+    assert rel_err(outs["node"][(15, False)], d["y_a"]) <= 1e-11
