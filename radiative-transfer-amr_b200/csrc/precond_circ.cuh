@@ -229,19 +229,37 @@ int rt_pc_apply(rtb200_ctx* ctx, const double* x, double* y, cudaStream_t st) {
         int rc = rt_pc_setup(ctx, st);
         if (rc) return rc;
     }
-    for (const Bucket& b : ctx->buckets) {
+    // buckets of an hp mesh run concurrently on the side streams, like the apply's
+    // (rt_launch_apply): fork from / join to the caller's stream
+    const size_t nb = ctx->buckets.size();
+    const size_t nside = nb > 1 ? std::min(ctx->side_streams.size(), nb - 1) : 0;
+    if (nside > 0) {
+        RT_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+        for (size_t s = 0; s < nside; ++s)
+            RT_CUDA(ctx, cudaStreamWaitEvent(ctx->side_streams[s], ctx->ev_fork, 0));
+    }
+    int rc_all = RTB200_OK;
+    for (size_t i = 0; i < nb && rc_all == RTB200_OK; ++i) {
+        const Bucket& b = ctx->buckets[ctx->bucket_order[i]];
+        const size_t slot = i % (nside + 1);
+        cudaStream_t q = slot == 0 ? st : ctx->side_streams[slot - 1];
         int rc = RTB200_EUNSUPPORTED;
         if (pc_circ_bucket(b)) {
 #define X(N_, NC_, P_)                                               \
     if (b.n == N_ && b.circ_nc == NC_ && b.circ_p == P_)             \
-        rc = launch_pc_circ<N_, NC_, P_>(ctx, b, x, y, st);
+        rc = launch_pc_circ<N_, NC_, P_>(ctx, b, x, y, q);
             RT_CIRC_COMBOS(X)
 #undef X
         } else {
-            rc = launch_pc_eig(ctx, b, x, y, st);
+            rc = launch_pc_eig(ctx, b, x, y, q);
         }
-        if (rc) return rc;
+        rc_all = rc;
     }
+    for (size_t s = 0; s < nside; ++s) {                     // always join, also after an error
+        cudaEventRecord(ctx->ev_join[s], ctx->side_streams[s]);
+        cudaStreamWaitEvent(st, ctx->ev_join[s], 0);
+    }
+    if (rc_all) return rc_all;
     if (ctx->dm.n_col > 0) {
         k_mask<<<ctx->dm.n_col, 256, 0, st>>>(ctx->dm, y, 1);
         ctx->launches++;
