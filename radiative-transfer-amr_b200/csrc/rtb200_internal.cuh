@@ -80,9 +80,7 @@ struct rtb200_ctx {
     int64_t launches = 0;
     int sm_count = 148;
 
-    // block-Jacobi preconditioner state (bjacobi.cu)
-    double* pc_inv = nullptr;      // [sum over columns nn * ntp * ntp]
-    int64_t* pc_off = nullptr;     // [n_col]
+    // node-wise block-Jacobi preconditioner state (precond_circ.cuh, precond_eig.cuh)
     bool pc_ready = false;
     double pc_shift = 1.0;         // extinction floor of the preconditioner, in units of 1 / min(dx, dy)
     double* pc_eig_pool = nullptr; // per-signature eigen tables (rtb200_pc_set_eig), in allocs
@@ -119,7 +117,7 @@ int rt_apply_with_halo(rtb200_ctx* ctx, unsigned terms, int interior_only, const
 // comm.cu
 int rt_allreduce_sum(rtb200_ctx* ctx, double* buf_dev, int count, cudaStream_t st);
 void rt_comm_destroy(rtb200_ctx* ctx);
-// bjacobi.cu
+// precond_circ.cuh / precond_eig.cuh (compiled into apply.cu)
 int rt_pc_setup(rtb200_ctx* ctx, cudaStream_t st);
 int rt_pc_apply(rtb200_ctx* ctx, const double* x, double* y, cudaStream_t st);
 void rt_pc_destroy(rtb200_ctx* ctx);
