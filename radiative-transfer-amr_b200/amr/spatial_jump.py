@@ -79,21 +79,41 @@ class SpatialJumpTables:
         pos = A.pos
         for F in range(4):
             lo, hi = (1, 3) if F % 2 == 0 else (0, 2)          # the coordinate along the face
-            n0_all = A.ny if F % 2 == 0 else A.nx
+            n0_all = (A.ny if F % 2 == 0 else A.nx).astype(np.int64)
             for slot in range(2):
                 g1 = A.nbr[:, F, slot].astype(np.int64)
-                for c in np.flatnonzero(g1 >= 0):
-                    d = int(g1[c])
-                    a0, b0, a1, b1 = pos[c, lo], pos[c, hi], pos[d, lo], pos[d, hi]
-                    n0, n1 = int(n0_all[c]), int(n0_all[d])
-                    fidx = c * 8 + F * 2 + slot
-                    key = ("s", n0, n1, _rel(a0, b0, a1, b1), float(min(b0 - a0, b1 - a1)))
-                    self.sp_off[fidx] = pool.block(
-                        key, lambda: interp_pair(a0, b0, n0, a1, b1, n1, lgl_rule))
+                cs = np.flatnonzero(g1 >= 0)
+                if cs.size == 0:
+                    continue
+                ds = g1[cs]
+                fidx = cs * 8 + F * 2 + slot
+                a0, b0, a1, b1 = pos[cs, lo], pos[cs, hi], pos[ds, lo], pos[ds, hi]
+                n0, n1 = n0_all[cs], n0_all[ds]
+                # one spatial block per distinct (node counts, relative position, length):
+                # grouped with numpy, built once per group
+                r0 = np.round((a1 - a0) / (b0 - a0), 9)
+                r1 = np.round((b1 - a0) / (b0 - a0), 9)
+                dmin = np.minimum(b0 - a0, b1 - a1)
+                keys = np.stack([n0.astype(np.float64), n1.astype(np.float64), r0, r1, dmin], axis=1)
+                uk, first, inv = np.unique(keys, axis=0, return_index=True, return_inverse=True)
+                inv = inv.reshape(-1)
+                offs = np.empty(len(uk), np.int64)
+                same = np.empty(len(uk), bool)
+                for u, t in enumerate(first):
+                    k0, k1 = int(n0[t]), int(n1[t])
+                    key = ("s", k0, k1, (float(r0[t]), float(r1[t])), float(dmin[t]))
+                    offs[u] = pool.block(key, lambda t=t, k0=k0, k1=k1: interp_pair(
+                        a0[t], b0[t], k0, a1[t], b1[t], k1, lgl_rule))
                     # same nodes on both sides: S0 = S1 = identity (the kernel's nodal fast path)
-                    same = n0 == n1 and _rel(a0, b0, a1, b1) == (0.0, 1.0)
-                    self.nb[fidx] = -n0 if same else max(n0, n1)
-                    s0, s1 = int(A.sig[c]), int(A.sig[d])
+                    same[u] = k0 == k1 and (float(r0[t]), float(r1[t])) == (0.0, 1.0)
+                self.sp_off[fidx] = offs[inv]
+                self.nb[fidx] = np.where(same[inv], -n0, np.maximum(n0, n1))
+                # angular pair tables, one per distinct (signature, neighbour signature)
+                s0s, s1s = A.sig[cs].astype(np.int64), A.sig[ds].astype(np.int64)
+                pk, pinv = np.unique(s0s * (len(A.sigs) + 1) + s1s, return_inverse=True)
+                poffs = np.empty(len(pk), np.int64)
+                for u, code in enumerate(pk):
+                    s0, s1 = int(code // (len(A.sigs) + 1)), int(code % (len(A.sigs) + 1))
                     if (s0, s1) not in pair_ids:
                         sg0, sg1 = A.sigs[s0], A.sigs[s1]
                         tab = -np.ones((len(sg0.keys), 2, 4), np.int32)
@@ -112,7 +132,8 @@ class SpatialJumpTables:
                         pair_ids[(s0, s1)] = n_pair
                         pair_parts.append(tab.reshape(-1))
                         n_pair += tab.size
-                    self.ap_off[fidx] = pair_ids[(s0, s1)]
+                    poffs[u] = pair_ids[(s0, s1)]
+                self.ap_off[fidx] = poffs[pinv.reshape(-1)]
         self.pool = pool.array()
         self.apair = np.concatenate(pair_parts).astype(np.int32) if pair_parts \
             else np.zeros(4, np.int32)
