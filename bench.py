@@ -513,8 +513,9 @@ def run_b200(args):
             gm = {"error": str(exc)} if gm is None else {**gm, "error": str(exc)}
 
     # ---- AMR error indicators on the resident vector (one launch each) -------- #
+    # (single rank: the indicators run on rank 0's mesh in the reference as well)
     amr = None
-    if not args.no_amr:
+    if not args.no_amr and world == 1:
         try:
             from rt_b200.amr.error_indicator import device_angular_jump, device_spatial_jump
             amr = {}
