@@ -206,3 +206,34 @@ def high_resolution_emulated(flat_lo, u_lo, flat_hi, u_hi, tables):
             err2.append(0.125 * dxy * dth * np.sum(w * (hi - v) ** 2))
             hr2[c] += 0.25 * dxy * (0.5 * dth) * np.sum(w * hi * hi)
     return np.array(err2), hr2
+
+
+def torch_angular_reference(torch, flat, x):
+    """Plain PyTorch FP64 restatement of k_err_angular for a UNIFORM mesh (one angular
+    signature of nc equal cells, all columns nx x ny): (cell_err2 [ncol * nc],
+    intg_xy [ncol * nt], intg_th [ncol * nn]) on x's device.  Used at the benchmark size,
+    where the oracle's Python loops are out of reach; pinned against the oracle on a small
+    mesh by tests/test_amr_cpu.py."""
+    from rt_b200.amr.error_indicator import lagrange_end_tables
+    ncol = flat.n_col
+    nx, ny = int(flat.col_nx[0]), int(flat.col_ny[0])
+    nn = nx * ny
+    nc, P = int(flat.sig_ncell[0]), int(flat.cell_nth[0])
+    nt = nc * P
+    assert flat.n_sig == 1 and int(flat.sig_ntp[0]) == nt and x.numel() == ncol * nn * nt
+    dev = x.device
+    bot, top = lagrange_end_tables()
+    bot_w = torch.from_numpy(bot[P, :P].copy()).to(dev)
+    top_w = torch.from_numpy(top[P, :P].copy()).to(dev)
+    w = torch.from_numpy(np.outer(flat.lgl_w[nx, :nx], flat.lgl_w[ny, :ny]).reshape(nn)).to(dev)
+    U = x.view(ncol, nn, nc, P)
+    tops = (U * top_w).sum(-1)
+    bots = (U * bot_w).sum(-1)
+    jl = bots - torch.roll(tops, 1, dims=2)          # lower neighbour: previous cell, periodic
+    ju = tops - torch.roll(bots, -1, dims=2)
+    err2 = 0.25 * (w[None, :, None] * (0.5 * (jl * jl + ju * ju))).sum(1)
+    dxy = torch.from_numpy(0.25 * flat.col_dx * flat.col_dy).to(dev)
+    ixy = dxy[:, None] * (w[None, :, None] * x.view(ncol, nn, nt)).sum(1)
+    wt = torch.from_numpy(flat.th_wt[:nt].copy()).to(dev)
+    ith = (x.view(ncol, nn, nt) * wt).sum(-1)
+    return err2.reshape(-1), ixy.reshape(-1), ith.reshape(-1)

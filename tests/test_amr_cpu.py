@@ -321,3 +321,19 @@ def test_error_analytic_host_glue_matches_reference(case, emulated_device):
     assert np.array_equal([ei.cols[ck].cells[kk].do_ref for ck, kk in order], g["an_cell_ref"])
     assert np.array_equal([ei.cols[ck].do_ref for ck in cols], g["an_col_ref"])
     assert [ei.cols[ck].cells[kk].ref_form for ck, kk in order] == [FORM[int(v)] for v in g["an_cell_form"]]
+
+
+def test_torch_angular_reference_equals_oracle_on_a_small_uniform_mesh():
+    """The PyTorch restatement used by the full-size GPU test, pinned against the oracle."""
+    import torch
+    from emulate import torch_angular_reference
+    from rt_b200 import configs
+    mesh = configs.build_mesh([3.0, 2.0], [False, False], [3, 3, 4], nref_ang=3, nref_spt=2)
+    flat = FlatMesh(MeshArrays.uniform([3.0, 2.0], 2, 3, [3, 3, 4]))
+    u = np.random.default_rng(4).standard_normal(mesh.get_ndof())
+    xs = np.zeros(flat.n_slab)
+    xs[flat.slab_index_of_dof()] = u
+    e2, ixy, ith = torch_angular_reference(torch, flat, torch.from_numpy(xs))
+    assert close(e2.numpy(), AO.angular_jump(mesh, u), 1e-12)
+    assert close(ixy.numpy(), AO.cell_intg_xy(mesh, u), 1e-12)
+    assert close(ith.numpy(), AO.col_intg_th(mesh, u), 1e-12)
