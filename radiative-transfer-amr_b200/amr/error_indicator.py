@@ -25,7 +25,6 @@ import ctypes as C
 import json
 
 import numpy as np
-from scipy.special import eval_legendre
 
 from .. import consts
 from .. import _lib as L
@@ -231,6 +230,33 @@ def device_high_resolution(op_lo, u_lo, op_hi, u_hi):
         op_lo.ctx, p(u_lo), op_hi.ctx, p(u_hi), *[p(x) for x in t], C.c_int32(max_cell),
         p(err2), p(hr2), op_lo._stream()))
     return err2[:n_cells].cpu().numpy(), hr2[:fl.n_col].cpu().numpy()
+
+
+def _legendre_coefficients_1d(vals, nodes, wts) -> np.ndarray:
+    """Coefficients c_m = (2m + 1)/2 sum_r w_r v_r P_m(x_r), m < n, of nodal values on an
+    n-point rule."""
+    nodes = np.asarray(nodes, dtype=np.float64)
+    n = nodes.shape[0]
+    V = np.polynomial.legendre.legvander(nodes, n - 1)                 # [node, degree]
+    return (np.arange(n) + 0.5) * (V.T @ (np.asarray(wts) * np.asarray(vals).reshape(n)))
+
+
+def _legendre_coefficients_2d(vals, xb, wx, yb, wy) -> np.ndarray:
+    """C[p, q] of the tensor-product Legendre expansion of nodal values vals[i, j]."""
+    xb, yb = np.asarray(xb, dtype=np.float64), np.asarray(yb, dtype=np.float64)
+    nx, ny = xb.shape[0], yb.shape[0]
+    Vx = np.polynomial.legendre.legvander(xb, nx - 1)
+    Vy = np.polynomial.legendre.legvander(yb, ny - 1)
+    W = np.asarray(wx).reshape(nx, 1) * np.asarray(wy).reshape(1, ny) * np.asarray(vals)
+    return (np.arange(nx) + 0.5)[:, None] * (Vx.T @ W @ Vy) * (np.arange(ny) + 0.5)[None, :]
+
+
+def _decay_rate(n: int, top_mode_sq: float) -> float:
+    """log((2n - 1) / (2 a^2)) / (2 log(n - 1)); +-inf / nan for n = 2 or a vanishing mode,
+    exactly as the reference's float arithmetic gives (its comparisons then decide)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return float(np.log((2. * n - 1.) / (2 * np.float64(top_mode_sq)))
+                     / (2. * np.log(np.float64(n - 1.))))
 
 
 def device_solution(proj):
@@ -486,53 +512,32 @@ class Error_Indicator:
         return self.proj.col_intg_th(col_key)
 
     def cell_hp_steer(self, col_key: int, cell_key: int) -> str:
-        """'p' when the highest angular Legendre coefficient of the spatially
-        integrated solution decays fast enough, else 'h' (``cell_hp_steer.py:16-48``)."""
+        """'p' when the highest angular Legendre mode of the spatially integrated solution
+        is small enough for its decay rate to beat the cell's order, else 'h'
+        (``cell_hp_steer.py:16-48``: l_p = log((2n - 1) / (2 |a_{n-1}|^2)) / (2 log(n - 1)),
+        'p' iff l_p - 1/2 >= n)."""
         cell = self.proj.cols[col_key].cells[cell_key]
         assert cell.is_lf
-        [nth] = cell.ndofs[:]
+        nth = cell.ndofs[0]
         _, _, _, _, thb, wth = quad_xyth(nnodes_th=nth)
-        thb = np.asarray(thb).reshape([1, nth])
-        wth = np.asarray(wth).reshape([1, nth])
-        uh_hat = np.asarray(self._cell_intg_xy(col_key, cell_key)).reshape([1, nth])
-        L_nthr = eval_legendre(nth - 1, thb)
-        a_nth = (2. * nth - 1.) / 2. * (wth * uh_hat) @ L_nthr.transpose()
-        ath_nth_sq = (a_nth[0, 0]) ** 2 * (2. / (2. * nth - 1.))
-        with np.errstate(divide="ignore", invalid="ignore"):
-            lp = np.log((2. * nth - 1.) / (2 * ath_nth_sq)) / (2. * np.log(nth - 1))
-        return "p" if lp - 0.5 >= float(nth) else "h"
+        coef = _legendre_coefficients_1d(self._cell_intg_xy(col_key, cell_key), thb, wth)
+        top_sq = coef[nth - 1] ** 2 * (2. / (2. * nth - 1.))
+        return "p" if _decay_rate(nth, top_sq) - 0.5 >= float(nth) else "h"
 
     def col_hp_steer(self, col_key: int) -> str:
-        """Spatial counterpart on the angle-integrated solution (``col_hp_steer.py:15-64``)."""
+        """Spatial counterpart on the angle-integrated solution (``col_hp_steer.py:15-64``):
+        the energy of the highest x-mode and of the highest y-mode of the tensor Legendre
+        expansion give two decay rates; 'p' iff their mean - 1/2 >= (nx + ny) / 2."""
         col = self.proj.cols[col_key]
         assert col.is_lf
-        [nx, ny] = col.ndofs[:]
-        xxb, wx, yyb, wy, _, _ = quad_xyth(nnodes_x=nx, nnodes_y=ny)
-        xxb = np.asarray(xxb).reshape([1, nx])
-        wx = np.asarray(wx).reshape([nx, 1])
-        yyb = np.asarray(yyb).reshape([1, ny])
-        wy = np.asarray(wy).reshape([1, ny])
-        w_uh = wx * wy * np.asarray(self._col_intg_th(col_key))
-
-        L_nxm = eval_legendre(nx - 1, xxb)
-        ndofs_y = np.arange(0, ny).reshape([1, ny])
-        L_jn = eval_legendre(ndofs_y.transpose(), yyb)
-        a_nxj = (2. * nx - 1.) * (2. * ndofs_y + 1.) / 4. * (L_nxm @ w_uh @ L_jn.transpose())
-        ax_nx_sq = 0
-        for jj in range(0, ny):
-            ax_nx_sq += (a_nxj[0, jj]) ** 2 * (2. / (2. * jj + 1.))
-
-        ndofs_x = np.arange(0, nx).reshape([nx, 1])
-        L_im = eval_legendre(ndofs_x, xxb)
-        L_nyn = eval_legendre(ny - 1, yyb)
-        a_iny = (2. * ndofs_x + 1.) * (2. * ny - 1.) / 4. * (L_im @ w_uh @ L_nyn.transpose())
-        ay_ny_sq = 0
-        for ii in range(0, nx):
-            ay_ny_sq += (a_iny[ii, 0]) ** 2 * (2. / (2. * ii + 1.))
-        with np.errstate(divide="ignore", invalid="ignore"):
-            term_0 = np.log((2. * nx - 1.) / (2 * ax_nx_sq)) / (2. * np.log(nx - 1.))
-            term_1 = np.log((2. * ny - 1.) / (2 * ay_ny_sq)) / (2. * np.log(ny - 1.))
-        lp = 0.5 * (term_0 + term_1)
+        nx, ny = col.ndofs
+        xb, wx, yb, wy, _, _ = quad_xyth(nnodes_x=nx, nnodes_y=ny)
+        C = _legendre_coefficients_2d(self._col_intg_th(col_key), xb, wx, yb, wy)
+        norm_y = 2. / (2. * np.arange(ny) + 1.)
+        norm_x = 2. / (2. * np.arange(nx) + 1.)
+        ax_sq = float(np.sum(C[nx - 1, :] ** 2 * norm_y))
+        ay_sq = float(np.sum(C[:, ny - 1] ** 2 * norm_x))
+        lp = 0.5 * (_decay_rate(nx, ax_sq) + _decay_rate(ny, ay_sq))
         return "p" if lp - 0.5 >= 0.5 * (nx + ny) else "h"
 
     # ---- refinement ---------------------------------------------------------- #
