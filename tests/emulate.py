@@ -237,3 +237,29 @@ def torch_angular_reference(torch, flat, x):
     wt = torch.from_numpy(flat.th_wt[:nt].copy()).to(dev)
     ith = (x.view(ncol, nn, nt) * wt).sum(-1)
     return err2.reshape(-1), ixy.reshape(-1), ith.reshape(-1)
+
+
+def pc_eig_emulated(flat, coef, eig_off, eig_pool, shift, r_slab):
+    """numpy transliteration of ``k_pc_eig`` + ``k_mask`` (csrc/precond_eig.cuh): z = mask .
+    W diag(1 / (mk_eff - ms lambda)) W^T r per (column, node), slab order."""
+    z = np.zeros_like(r_slab)
+    for c in range(flat.n_col):
+        nx, ny = int(flat.col_nx[c]), int(flat.col_ny[c])
+        nn = nx * ny
+        sg = int(flat.col_sig[c])
+        nt, ntp = int(flat.sig_nt[sg]), int(flat.sig_ntp[sg])
+        off = int(flat.col_slab_off[c])
+        o = int(eig_off[sg])
+        lam = eig_pool[o:o + nt]
+        W = eig_pool[o + nt:o + nt + nt * nt].reshape(nt, nt)
+        Wt = eig_pool[o + nt + nt * nt:o + nt + 2 * nt * nt].reshape(nt, nt)
+        dx, dy = flat.col_dx[c], flat.col_dy[c]
+        co = int(flat.col_coef_off[c])
+        for n in range(nn):
+            i, j = divmod(n, ny)
+            mk = coef[co + n] + shift * 0.25 * dx * dy * flat.lgl_w[nx, i] * flat.lgl_w[ny, j] / min(dx, dy)
+            ms = coef[co + nn + n]
+            r = r_slab[off + n * ntp: off + n * ntp + nt]
+            t = (r @ W) / (mk - ms * lam)
+            z[off + n * ntp: off + n * ntp + nt] = t @ Wt
+    return z

@@ -268,3 +268,39 @@ def test_pc_eig_tables_invert_the_preconditioner_blocks():
                 assert np.max(np.abs(Binv @ B - np.eye(nt))) < 1e-10
     # a non-symmetric kernel is refused
     assert T.pc_eig_tables(G + np.triu(np.ones_like(G), 1) * 1e-3, wt) is None
+
+
+@pytest.mark.parametrize("case", ["hp_mixed", "test_mesh_script", "periodic_small"])
+def test_pc_eig_tables_through_kernel_emulation(case):
+    """Eigen pool, coefficient samples and slab layout, walked as k_pc_eig walks them
+    (tests/emulate.py), reproduce a sparse direct solve with the oracle's M - S (extinction
+    floored column by column like the kernel does)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from conftest import load_golden
+    from oracle import rt_oracle as O
+    from rt_b200.dg.flatmesh import FlatMesh
+    from rt_b200.rt.operator import (build_circ_pool, build_g_pool, build_pc_eig_pool,
+                                     sample_coefficients)
+    mesh, d, prob = load_golden(case)
+    flat = FlatMesh(mesh)
+    g_off, g_pool = build_g_pool(flat, prob.Phi)
+    eig_off, eig_pool = build_pc_eig_pool(flat, g_off, g_pool, build_circ_pool(flat, g_off, g_pool))
+    assert np.all(eig_off >= 0)
+    coef = sample_coefficients(flat, prob.kappa, prob.sigma)
+    shift = 0.5
+    ref = O.assemble(mesh, prob.kappa, prob.sigma, prob.Phi)
+    one = O.assemble(mesh, lambda x, y: 1.0 + 0 * x + 0 * y, lambda x, y: 0 * x + 0 * y, prob.Phi)
+    coff, csize, n = O.col_offsets(mesh)
+    scale = np.zeros(n)
+    for ck, col in mesh.cols.items():
+        scale[coff[ck]:coff[ck] + csize[ck]] = shift / min(col.pos[2] - col.pos[0], col.pos[3] - col.pos[1])
+    MS = (ref["MS"] + sp.diags(scale) @ one["MS"]).tocsc()
+    mask = ref["mask"].astype(bool)
+    r = np.random.default_rng(5).standard_normal(n) * mask
+    idx = flat.slab_index_of_dof()
+    r_slab = np.zeros(flat.n_slab)
+    r_slab[idx] = r
+    z = E.pc_eig_emulated(flat, coef, eig_off, eig_pool, shift, r_slab)[idx] * mask
+    z_ref = spla.spsolve(MS, r) * mask
+    assert np.linalg.norm(z - z_ref) <= 1e-10 * np.linalg.norm(z_ref)
