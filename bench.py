@@ -53,6 +53,7 @@ WORKLOADS = {
     # seeded synthetic hp-refined meshes (small twins of BASELINE configs[4]):
     # (spatial base level, -, -); hanging nodes, degree jumps, non-uniform angular meshes
     "c5-small": (6, None, None),      # ~3.7e6 DoF
+    "c5-512": (-7, None, None),       # level 7 base, two levels of h-refinement: 512 x 512 finest
     "c5": (7, None, None),            # ~1.5e7 DoF
 }
 LS = [3.0, 2.0]
@@ -211,6 +212,7 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     ns, na, nd = WORKLOADS[args.workload]
+    ns = abs(ns)
     arm = CpuArm(cores, (min(ns, 4), na or 5, nd or [5, 5, 5]))
     for _ in range(max(args.warmup, 1)):
         arm.step()
@@ -254,7 +256,8 @@ def run_b200(args):
     prob = configs.two_strong_scatterers(LS)
     t0 = time.perf_counter()
     if na is None:
-        hp_mesh = configs.hp_synthetic(LS, level=ns)
+        hp_mesh = configs.hp_synthetic(LS, level=abs(ns), depth=2 if ns < 0 else 1)
+        ns = abs(ns)
         flat = FlatMesh(hp_mesh, rank=rank, nranks=world)
     else:
         flat = FlatMesh(MeshArrays.uniform(LS, ns, na, nd), rank=rank, nranks=world)

@@ -42,7 +42,8 @@ def build_mesh(Ls, pbcs, ndofs, nref_ang, nref_spt, has_th=True, **_) -> Mesh:
 
 
 def hp_synthetic(Ls=(3.0, 2.0), level: int = 4, seed: int = 20240817, ndofs=(3, 3, 3),
-                 frac_h: float = 0.3, frac_p: float = 0.35, frac_ang: float = 0.3) -> Mesh:
+                 frac_h: float = 0.3, frac_p: float = 0.35, frac_ang: float = 0.3,
+                 depth: int = 1) -> Mesh:
     """Seeded synthetic hp-refined mesh (a small twin of BASELINE.json configs[4], built
     with the same ``Mesh.ref_col`` / ``ref_cell`` calls the reference's AMR loop issues, so
     2:1 balance and degree-jump rules are the reference's own): uniform spatial level
@@ -50,13 +51,20 @@ def hp_synthetic(Ls=(3.0, 2.0), level: int = 4, seed: int = 20240817, ndofs=(3, 
     space, ``frac_p`` of the columns p-refined in space (twice for a third of them), and
     in a random ``frac_ang`` of the columns some angular cells h- or p-refined.  The result
     has hanging nodes, spatial degree jumps and non-uniform angular meshes (dense
-    scattering path) next to untouched columns (block-circulant path)."""
+    scattering path) next to untouched columns (block-circulant path).  ``depth`` > 1 repeats
+    the spatial h-refinement on a quarter of the columns of the finest level, ``depth - 1``
+    more times (``level = 7, depth = 2``: 512 x 512 finest resolution, BASELINE configs[4])."""
     rng = np.random.default_rng(seed)
     mesh = build_mesh(Ls, [False, False], list(ndofs), nref_ang=3, nref_spt=level)
     keys = sorted(mesh.cols.keys())
     for k in rng.choice(keys, size=int(frac_h * len(keys)), replace=False):
         if int(k) in mesh.cols:
             mesh.ref_col(int(k), kind="spt", form="h")
+    for d in range(1, depth):
+        fine = sorted(k for k, c in mesh.cols.items() if c.lv == level + d)
+        for k in rng.choice(fine, size=int(0.25 * len(fine)), replace=False):
+            if int(k) in mesh.cols:
+                mesh.ref_col(int(k), kind="spt", form="h")
     keys = sorted(mesh.cols.keys())
     for n, k in enumerate(rng.choice(keys, size=int(frac_p * len(keys)), replace=False)):
         if int(k) in mesh.cols:

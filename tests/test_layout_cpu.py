@@ -217,18 +217,20 @@ def test_partitioned_apply_equals_single_rank(name, nranks):
     assert sum(f.n_dof for f in flats) == d["x"].size
 
 
-def test_hp_synthetic_mesh_tables_reproduce_the_oracle():
+@pytest.mark.parametrize("depth", [1, 2])
+def test_hp_synthetic_mesh_tables_reproduce_the_oracle(depth):
     """The seeded hp-refined benchmark mesh (configs.hp_synthetic, the small twin of
-    BASELINE configs[4]): the flattened tables, run through the numpy emulation of the
-    kernel, reproduce the oracle's assembled operator term by term; the generator is
-    deterministic."""
+    BASELINE configs[4]; depth 2: two levels of spatial refinement below the base): the
+    flattened tables, run through the numpy emulation of the kernel, reproduce the oracle's
+    assembled operator term by term; the generator is deterministic."""
     import emulate as E
     from oracle import rt_oracle as O
     from rt_b200 import configs
     from rt_b200.dg.flatmesh import FlatMesh
     prob = configs.two_strong_scatterers()
-    mesh = configs.hp_synthetic(level=2)
-    assert configs.hp_synthetic(level=2) == mesh                      # seeded: reproducible
+    mesh = configs.hp_synthetic(level=2, depth=depth)
+    assert configs.hp_synthetic(level=2, depth=depth) == mesh         # seeded: reproducible
+    assert max(c.lv for c in mesh.cols.values()) == 2 + depth
     ref = O.assemble(mesh, prob.kappa, prob.sigma, prob.Phi)
     f = FlatMesh(mesh)
     assert len(f.arrays.sigs) > 1 and f.stats()["exy_tables"] > 0    # really hp: several angular meshes, mortars
