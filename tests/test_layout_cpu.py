@@ -205,7 +205,7 @@ def _partitioned_apply(mesh, prob, x, nranks, terms=15, interior_only=False):
 
 
 @pytest.mark.parametrize("name", ["c1_uniform", "hp_mixed", "periodic_small"])
-@pytest.mark.parametrize("nranks", [2, 3, 8])
+@pytest.mark.parametrize("nranks", [2, 3, 8, 40])   # 40 > columns: empty ranks
 def test_partitioned_apply_equals_single_rank(name, nranks):
     mesh, d, prob = load_golden(name)
     y, flats = _partitioned_apply(mesh, prob, d["x"], nranks)
