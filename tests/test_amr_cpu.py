@@ -337,3 +337,50 @@ def test_torch_angular_reference_equals_oracle_on_a_small_uniform_mesh():
     assert close(e2.numpy(), AO.angular_jump(mesh, u), 1e-12)
     assert close(ixy.numpy(), AO.cell_intg_xy(mesh, u), 1e-12)
     assert close(ith.numpy(), AO.col_intg_th(mesh, u), 1e-12)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_indicator_amr_cycles_equal_live_reference(seed, have_reference):
+    """Three AMR cycles driven by error_random (same generator state on both sides) on a
+    random field: flags, hp-steering decisions and the mesh ref_by_ind returns are identical
+    to the unmodified reference package's, cycle after cycle."""
+    if not have_reference:
+        pytest.skip("/root/reference is not mounted (GPU box)")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_amr", os.path.join(GOLDEN, "make_golden_amr.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    EI = mg.load_ref_amr()
+    from dg.mesh import Mesh as RefMesh
+    from dg.projection import Projection as RefProjection
+    from rt_b200.dg.mesh import Mesh
+    from test_dg_cpu import _leaves
+    rng0 = np.random.default_rng(50 + seed)
+    ndofs = [int(rng0.integers(2, 5))] * 2 + [int(rng0.integers(2, 5))]
+    kind = ["ang", "spt", "all"][seed % 3]
+    meshes = []
+    for M in (Mesh, RefMesh):
+        m = M([3., 2.], [False, False], ndofs, True)
+        for _ in range(2):
+            m.ref_mesh(kind="ang", form="h")
+        m.ref_mesh(kind="spt", form="h")
+        meshes.append(m)
+    mine, ref = meshes
+    for cycle in range(3):
+        u = np.random.default_rng(seed * 10 + cycle).standard_normal(mine.get_ndof())
+        p_mine = Projection(mine).from_vector(u)
+        p_ref = RefProjection(ref)
+        p_ref.from_vector(u)
+        e_mine = Error_Indicator(p_mine, ref_kind=kind, ref_form="hp", ref_tol=[0.6, 0.6])
+        e_ref = EI.Error_Indicator(p_ref, ref_kind=kind, ref_form="hp", ref_tol=[0.6, 0.6])
+        e_mine.error_random(np.random.default_rng(777 + cycle))
+        e_ref.error_random(np.random.default_rng(777 + cycle))
+        for ck, col in sorted(mine.cols.items()):
+            assert (e_mine.cols[ck].do_ref, e_mine.cols[ck].ref_form, e_mine.cols[ck].error) == \
+                (e_ref.cols[ck].do_ref, e_ref.cols[ck].ref_form, e_ref.cols[ck].error)
+            for kk in col.cells:
+                a, b = e_mine.cols[ck].cells[kk], e_ref.cols[ck].cells[kk]
+                assert (a.do_ref, a.ref_form, a.error) == (b.do_ref, b.ref_form, b.error)
+        assert e_mine.error_to_resolve == e_ref.error_to_resolve
+        mine, ref = e_mine.ref_by_ind(), e_ref.ref_by_ind()
+        assert _leaves(mine) == _leaves(ref)

@@ -188,3 +188,40 @@ def test_index_maps_and_masks(case):
     assert np.array_equal(get_bdry_mask(mesh), ~d["mask"])
     vi, vb = split_vector(d["x"], mask)
     assert np.array_equal(merge_vectors(vi, vb, mask), d["x"])
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_refinement_scripts_equal_live_reference(seed, have_reference):
+    """Seeded random sequences of the calls the AMR loop issues (ref_col spt / ang / all with
+    h, p, hp; ref_cell with h, p, hp) applied to this Mesh and to the reference's: identical
+    leaves -- keys, extents, levels, orders, quadrants, neighbour keys -- after every script
+    (2:1 balance and degree-jump cascades included)."""
+    if not have_reference:
+        pytest.skip("/root/reference is not mounted (GPU box)")
+    from oracle import ref_harness as H
+    from rt_b200.dg.mesh import Mesh
+    H.load()
+    from dg.mesh import Mesh as RefMesh
+    rng = np.random.default_rng(1000 + seed)
+    pbcs = [bool(rng.integers(2)), bool(rng.integers(2))]
+    ndofs = [int(rng.integers(2, 5))] * 2 + [int(rng.integers(2, 5))]
+    meshes = [M([3., 2.], pbcs, ndofs, True) for M in (Mesh, RefMesh)]
+    for m in meshes:
+        for _ in range(2):
+            m.ref_mesh(kind="ang", form="h")
+        m.ref_mesh(kind="spt", form="h")
+    for _ in range(14):
+        mine = meshes[0]
+        ck = int(rng.choice(sorted(mine.cols)))
+        if rng.random() < 0.5:
+            kind = str(rng.choice(["spt", "ang", "all"]))
+            form = str(rng.choice(["h", "p", "hp"]))
+            for m in meshes:
+                m.ref_col(ck, kind=kind, form=form)
+        else:
+            kk = int(rng.choice(sorted(mine.cols[ck].cells)))
+            form = str(rng.choice(["h", "p", "hp"]))
+            for m in meshes:
+                m.ref_cell(ck, kk, form=form)
+        assert _leaves(meshes[0]) == _leaves(meshes[1])
+    assert meshes[0].get_ndof() == meshes[1].get_ndof()
