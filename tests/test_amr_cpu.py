@@ -384,3 +384,58 @@ def test_random_indicator_amr_cycles_equal_live_reference(seed, have_reference):
         assert e_mine.error_to_resolve == e_ref.error_to_resolve
         mine, ref = e_mine.ref_by_ind(), e_ref.ref_by_ind()
         assert _leaves(mine) == _leaves(ref)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_jump_indicators_on_random_hp_meshes_equal_live_reference(seed, have_reference, emulated_device):
+    """Random hp meshes (random refinement scripts) and random fields: the angular- and
+    spatial-jump pipelines (host tables + kernel emulations + host glue) against the
+    unmodified reference package run live."""
+    if not have_reference:
+        pytest.skip("/root/reference is not mounted (GPU box)")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_amr", os.path.join(GOLDEN, "make_golden_amr.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    EI = mg.load_ref_amr()
+    from dg.mesh import Mesh as RefMesh
+    from dg.projection import Projection as RefProjection
+    from rt_b200.dg.mesh import Mesh
+    rng = np.random.default_rng(300 + seed)
+    ndofs = [int(rng.integers(2, 5))] * 2 + [int(rng.integers(2, 5))]
+    meshes = [M([3., 2.], [bool(seed & 1), False], ndofs, True) for M in (Mesh, RefMesh)]
+    for m in meshes:
+        for _ in range(2):
+            m.ref_mesh(kind="ang", form="h")
+        m.ref_mesh(kind="spt", form="h")
+    for _ in range(8):
+        ck = int(rng.choice(sorted(meshes[0].cols)))
+        if rng.random() < 0.5:
+            kind, form = str(rng.choice(["spt", "ang", "all"])), str(rng.choice(["h", "p", "hp"]))
+            for m in meshes:
+                m.ref_col(ck, kind=kind, form=form)
+        else:
+            kk, form = int(rng.choice(sorted(meshes[0].cols[ck].cells))), str(rng.choice(["h", "p"]))
+            for m in meshes:
+                m.ref_cell(ck, kk, form=form)
+    mine, ref = meshes
+    u = rng.standard_normal(mine.get_ndof())
+    p_ref = RefProjection(ref)
+    p_ref.from_vector(u)
+    cols = sorted(mine.cols)
+    order = [(ck, kk) for ck in cols for kk in sorted(mine.cols[ck].cells)]
+    for method, tol in (("error_angular_jump", 1e-11), ("error_spatial_jump", 1e-10)):
+        e_mine = Error_Indicator(Projection(mine).from_vector(u), ref_kind="all", ref_form="hp",
+                                 ref_tol=[0.5, 0.5])
+        e_ref = EI.Error_Indicator(p_ref, ref_kind="all", ref_form="hp", ref_tol=[0.5, 0.5])
+        getattr(e_mine, method)()
+        getattr(e_ref, method)()
+        assert close([e_mine.cols[ck].error for ck in cols], [e_ref.cols[ck].error for ck in cols], tol)
+        assert close(e_mine.error, e_ref.error, tol)
+        assert [e_mine.cols[ck].do_ref for ck in cols] == [e_ref.cols[ck].do_ref for ck in cols]
+        assert [e_mine.cols[ck].ref_form for ck in cols] == [e_ref.cols[ck].ref_form for ck in cols]
+        if method == "error_angular_jump":
+            assert close([e_mine.cols[ck].cells[kk].error for ck, kk in order],
+                         [e_ref.cols[ck].cells[kk].error for ck, kk in order], tol)
+            assert [e_mine.cols[ck].cells[kk].do_ref for ck, kk in order] == \
+                [e_ref.cols[ck].cells[kk].do_ref for ck, kk in order]
