@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define RTB200_ABI_VERSION 5
+#define RTB200_ABI_VERSION 6
 
 /* error codes */
 #define RTB200_OK            0
@@ -169,6 +169,12 @@ typedef struct rtb200_flatmesh {
     const int32_t* sig_circ_p;    /* [n_sig] P                                    */
     const int64_t* sig_circ_off;  /* [n_sig] even offset into circ_pool or -1     */
     int64_t n_circ_pool;  const double*  circ_pool;
+
+    /* per (column, face, slot) [n_col*8]: LOCAL index of the neighbour column across the face
+       (Column.nhbr_keys, class_Mesh.py:39-52) when it is owned by this rank and geometrically
+       adjacent; -1: none; -2: owned by another rank (ghost trace); -3: periodic wrap-around.
+       Used by the transport-sweep preconditioner to order the columns upwind. */
+    const int32_t* face_nbr;
 } rtb200_flatmesh;
 
 typedef struct rtb200_gmres_params {
@@ -179,9 +185,13 @@ typedef struct rtb200_gmres_params {
     double  divtol;         /* reference: sqrt(consts.INF)                                  */
     int32_t orth;           /* 0: classical Gram-Schmidt, refine if needed (DGKS);
                                1: always two passes; 2: never refine (PETSc default)        */
-    int32_t pc;             /* 0: none; 1: block-Jacobi over (node, column) angular blocks  */
+    int32_t pc;             /* RTB200_PC_*: 0 none, 1 node-wise (M - S)^-1, 2 transport sweep,
+                               3 element-wise block-Jacobi (the sweep without upwind coupling) */
     int32_t x0_nonzero;     /* reference: 1 (solve.py:97)                                   */
     int32_t record_history; /* 1: write residual norms to hist                              */
+    int32_t pc_side;        /* 0: left (KSPGMRES default; preconditioned residual norms);
+                               1: right, flexible (KSPFGMRES, solve.py:83: the z_k = M^-1 v_k are
+                                  stored, unpreconditioned residual norms)                   */
 } rtb200_gmres_params;
 
 typedef struct rtb200_gmres_result {
@@ -231,10 +241,19 @@ int  rtb200_apply(rtb200_ctx* ctx, unsigned terms, int interior_only,
  *      b, x: slab order, zero on boundary entries and pads.
  *      work: rtb200_gmres_work_bytes() bytes of device memory.
  *      hist: host array of max_it+1 doubles or NULL. -------------------- */
-int64_t rtb200_gmres_work_bytes(const rtb200_ctx* ctx, int restart);
+int64_t rtb200_gmres_work_bytes(const rtb200_ctx* ctx, int restart, int pc_side);
 int  rtb200_gmres(rtb200_ctx* ctx, const double* b_dev, double* x_dev,
                   const rtb200_gmres_params* prm, rtb200_gmres_result* res,
                   double* hist_host, void* work_dev, int64_t work_bytes, void* stream);
+
+/* preconditioner kinds (rtb200_gmres_params.pc, rtb200_pc_set_type) */
+#define RTB200_PC_NONE     0
+#define RTB200_PC_NODE     1     /* node-wise block-Jacobi: (M - S)^-1 per (column, spatial node)      */
+#define RTB200_PC_SWEEP    2     /* transport sweep: (M + BC - IC)^-1 by upwind-ordered block
+                                    Gauss-Seidel over (column, angle) elements -- what PETSc's
+                                    bjacobi + ILU(0) (solve.py:93-95) approximates per rank        */
+#define RTB200_PC_ELEMENT  3     /* element-wise block-Jacobi: the (column, angle) diagonal blocks
+                                    of M + BC - IC only (north star, subsystem 4)                  */
 
 /* ---- preconditioner: z = mask . (M - S)^{-1} r, the inverse of the reference's
  *      "preconditioner matrix" (preconditioner_matrix.py:22-267, block diagonal
@@ -256,6 +275,29 @@ int  rtb200_pc_set_eig(rtb200_ctx* ctx, const int64_t* sig_eig_off, int32_t n_si
 /* extinction floor kappa_eff = kappa + shift / min(dx, dy) used inside the preconditioner
  * (vacuum regions make M - S singular); default 1, 0 = exact (M - S)^{-1} */
 int  rtb200_pc_set_shift(rtb200_ctx* ctx, double shift);
+
+/* ---- transport-aware preconditioners (RTB200_PC_SWEEP / RTB200_PC_ELEMENT).
+ *      z = mask . T~^{-1} r with T~ = M~ + BC - IC: the streaming part of the operator
+ *      (mass_matrix.py, interior_convection_matrix.py, boundary_convection_matrix.py) with the
+ *      extinction of a column replaced by the mid-range of its nodal samples.  T~ is block lower
+ *      triangular when the (column, quadrant) elements are ordered upwind (the inflow faces of a
+ *      quadrant only see columns that come earlier), so T~^{-1} r is ONE sweep: the library
+ *      orders the elements topologically (levels of independent elements, one launch per level)
+ *      and solves each (column, angle) diagonal block -- nx ny unknowns -- by tensor-product
+ *      fast diagonalisation of the 1-D upwind operators, followed by n_corr defect-correction
+ *      steps with the true nodal extinction.  Off-rank (ghost) and periodic wrap-around inflow is
+ *      lagged (block Jacobi across ranks, like PETSc's bjacobi).
+ *      rtb200_pc_set_fd uploads the 1-D tables (built by rt_b200.rt.tables.fd_tables): for every
+ *      n = 1..RTB200_MAX_NXY and variant v = (flow sign < 0) + 2 (inflow end node removed)
+ *      at fd_off[n * 4 + v]:  [lambda: n][V: n x n, row i][L = V^-1 W^-1: n x n, row alpha],
+ *      complex (re, im) doubles, for the eigen-decomposition W^-1 B = V diag(lambda) V^-1 of the
+ *      1-D operator B = -S + (outflow end node).  HOST pointers, copied.
+ *      rtb200_pc_set_type selects what rtb200_pc_apply computes (default RTB200_PC_NODE). --- */
+int  rtb200_pc_set_fd(rtb200_ctx* ctx, const int64_t* fd_off, int32_t n_off,
+                      const double* fd_pool, int64_t n_pool);
+int  rtb200_pc_set_type(rtb200_ctx* ctx, int pc_type, int n_corr);
+/* sweep statistics after the first use: levels (launches per sweep), elements */
+int  rtb200_pc_sweep_info(rtb200_ctx* ctx, int32_t* n_levels, int64_t* n_items);
 
 /* ---- multi-GPU: one process per GPU; columns split like the reference's
  *      np.array_split(sorted keys, size)[rank] (mass_matrix.py:50-51).

@@ -9,11 +9,12 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_NXY = 12
 MAX_NTH = 16
 
 TERM_MASS, TERM_SCAT, TERM_ICONV, TERM_BCONV, TERM_ALL = 1, 2, 4, 8, 15
+PC_NONE, PC_NODE, PC_SWEEP, PC_ELEMENT = 0, 1, 2, 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "librtb200.so")
@@ -51,13 +52,15 @@ class FlatMeshC(C.Structure):
         ("n_send", C.c_int64), ("send_src", _i64p),
         ("sig_circ_nc", _i32p), ("sig_circ_p", _i32p), ("sig_circ_off", _i64p),
         ("n_circ_pool", C.c_int64), ("circ_pool", _f64p),
+        ("face_nbr", _i32p),
     ]
 
 
 class GmresParams(C.Structure):
     _fields_ = [("restart", C.c_int32), ("max_it", C.c_int32), ("rtol", C.c_double),
                 ("atol", C.c_double), ("divtol", C.c_double), ("orth", C.c_int32),
-                ("pc", C.c_int32), ("x0_nonzero", C.c_int32), ("record_history", C.c_int32)]
+                ("pc", C.c_int32), ("x0_nonzero", C.c_int32), ("record_history", C.c_int32),
+                ("pc_side", C.c_int32)]
 
 
 class GmresResult(C.Structure):
@@ -80,7 +83,7 @@ SYMBOLS = {
     "rtb200_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "rtb200_apply": (C.c_int, [C.c_void_p, C.c_uint, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_void_p]),
-    "rtb200_gmres_work_bytes": (C.c_int64, [C.c_void_p, C.c_int]),
+    "rtb200_gmres_work_bytes": (C.c_int64, [C.c_void_p, C.c_int, C.c_int]),
     "rtb200_gmres": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(GmresParams),
                                C.POINTER(GmresResult), _f64p, C.c_void_p, C.c_int64,
                                C.c_void_p]),
@@ -90,6 +93,9 @@ SYMBOLS = {
     "rtb200_pc_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rtb200_pc_set_shift": (C.c_int, [C.c_void_p, C.c_double]),
     "rtb200_pc_set_eig": (C.c_int, [C.c_void_p, _i64p, C.c_int32, _f64p, C.c_int64]),
+    "rtb200_pc_set_fd": (C.c_int, [C.c_void_p, _i64p, C.c_int32, _f64p, C.c_int64]),
+    "rtb200_pc_set_type": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "rtb200_pc_sweep_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "rtb200_err_angular_jump": (C.c_int, [C.c_void_p] + [C.c_void_p] * 8 + [C.c_int32] * 2
                                 + [C.c_void_p] * 4),
     "rtb200_err_spatial_jump": (C.c_int, [C.c_void_p] * 9),

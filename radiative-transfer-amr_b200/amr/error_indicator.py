@@ -264,16 +264,18 @@ def device_solution(proj):
     on it, else a table-only operator for its mesh and an upload of its values."""
     dev = getattr(proj, "_device", None)
     if dev is not None:
-        op, u_slab = dev
+        op, u_slab, stamp = dev
+        # the cached pair is only valid while the projection still holds the values it was
+        # made from (from_vector clears it; in-place edits of cell.vals change the checksum)
         if getattr(op, "ctx", None) is not None and op.ctx.value and \
-                op.flat.nranks == 1 and op.n == proj.mesh.get_ndof():
+                op.flat.nranks == 1 and op.n == proj.mesh.get_ndof() and stamp == proj.checksum():
             return op, u_slab
     from ..rt.operator import RTOperator
     zero = lambda x, y: np.zeros(np.broadcast(x, y).shape)          # noqa: E731
     iso = lambda th0, th1: 1. / (2. * consts.PI) + 0. * (th0 - th1)  # noqa: E731
     op = RTOperator(proj.mesh, zero, zero, iso)
     u_slab = op.to_slab(proj.to_vector())
-    proj._device = (op, u_slab)
+    proj._device = (op, u_slab, proj.checksum())
     return op, u_slab
 
 

@@ -473,6 +473,10 @@ int rt_launch_apply(rtb200_ctx* ctx, unsigned terms, int interior_only, const do
 // stream; the few columns next to another rank's slab follow once the traces have landed.
 int rt_apply_with_halo(rtb200_ctx* ctx, unsigned terms, int interior_only, const double* x,
                        double* y, cudaStream_t st) {
+    if ((terms & RTB200_TERM_BCONV) && !ctx->peer_rank.empty() && (ctx->nranks <= 1 || !ctx->nccl_comm))
+        return rt_fail(ctx, RTB200_ESTATE,
+                       "this rank's mesh reads face traces of other ranks but no communicator is "
+                       "initialised (rtb200_comm_init): the ghost traces would be zero");
     if (!(terms & RTB200_TERM_BCONV) || ctx->nranks <= 1 || ctx->peer_rank.empty())
         return rt_launch_apply(ctx, terms, interior_only, x, y, st);
     int rc;

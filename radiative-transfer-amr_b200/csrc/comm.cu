@@ -140,15 +140,20 @@ extern "C" int rtb200_halo_exchange(rtb200_ctx* ctx, const double* x_slab_dev, v
     }
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
     RT_NCCL(ctx, api, api->GroupStart());
-    for (size_t p = 0; p < ctx->peer_rank.size(); ++p) {
+    ncclResult_t bad = ncclSuccess;
+    for (size_t p = 0; p < ctx->peer_rank.size() && bad == ncclSuccess; ++p) {
         const int64_t ns = ctx->peer_send0[p + 1] - ctx->peer_send0[p];
         const int64_t nr = ctx->peer_recv0[p + 1] - ctx->peer_recv0[p];
         if (ns > 0)
-            RT_NCCL(ctx, api, api->Send(ctx->send_dev + ctx->peer_send0[p], (size_t)ns, ncclDouble,
-                                        ctx->peer_rank[p], comm, st));
-        if (nr > 0)
-            RT_NCCL(ctx, api, api->Recv(ctx->ghost_dev + ctx->peer_recv0[p], (size_t)nr, ncclDouble,
-                                        ctx->peer_rank[p], comm, st));
+            bad = api->Send(ctx->send_dev + ctx->peer_send0[p], (size_t)ns, ncclDouble,
+                            ctx->peer_rank[p], comm, st);
+        if (nr > 0 && bad == ncclSuccess)
+            bad = api->Recv(ctx->ghost_dev + ctx->peer_recv0[p], (size_t)nr, ncclDouble,
+                            ctx->peer_rank[p], comm, st);
+    }
+    if (bad != ncclSuccess) {
+        api->GroupEnd();                       // never leave the group open
+        return nccl_fail(ctx, api, bad, "ncclSend / ncclRecv (halo exchange)");
     }
     RT_NCCL(ctx, api, api->GroupEnd());
     return RTB200_OK;

@@ -53,6 +53,7 @@ static void free_tables(rtb200_ctx* ctx) {
     ctx->send_src_dev = nullptr;
     ctx->have_mesh = false;
     rt_pc_destroy(ctx);
+    rt_sweep_destroy(ctx);
 }
 
 extern "C" void rtb200_destroy(rtb200_ctx* ctx) {
@@ -146,6 +147,23 @@ extern "C" int rtb200_set_mesh(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
     UP(g_pool, m->n_g_pool); UP(exy_pool, m->n_exy_pool); UP(eth_pool, m->n_eth_pool);
     UP(acpl_pool, m->n_acpl_pool);
     UP(coef, m->n_coef);
+    if (!m->face_nbr && nc > 0) return rt_fail(ctx, RTB200_EINVAL, "null table face_nbr");
+    if (!m->lgl_w || !m->lgl_s) return rt_fail(ctx, RTB200_EINVAL, "missing LGL tables");
+    UP(face_nbr, nc * 8);
+    // host copies for the sweep schedule (precond_sweep.cu)
+    ctx->h_col_nx.assign(m->col_nx, m->col_nx + nc);
+    ctx->h_col_ny.assign(m->col_ny, m->col_ny + nc);
+    ctx->h_col_sig.assign(m->col_sig, m->col_sig + nc);
+    ctx->h_col_bdry.assign(m->col_bdry, m->col_bdry + nc);
+    ctx->h_face_nbr.assign(m->face_nbr, m->face_nbr + nc * 8);
+    ctx->h_col_coef_off.assign(m->col_coef_off, m->col_coef_off + nc);
+    ctx->h_col_dx.assign(m->col_dx, m->col_dx + nc);
+    ctx->h_col_dy.assign(m->col_dy, m->col_dy + nc);
+    ctx->h_sig_nt.assign(m->sig_nt, m->sig_nt + m->n_sig);
+    ctx->h_sig_th0.assign(m->sig_th0, m->sig_th0 + m->n_sig);
+    ctx->h_th_bits.assign(m->th_bits, m->th_bits + m->n_theta_pool);
+    ctx->h_lgl_w.assign(m->lgl_w, m->lgl_w + (RTB200_MAX_NXY + 1) * RTB200_MAX_NXY);
+    ctx->h_lgl_s.assign(m->lgl_s, m->lgl_s + (RTB200_MAX_NXY + 1) * RTB200_MAX_NXY * RTB200_MAX_NXY);
     ctx->coef_dev = const_cast<double*>(ctx->dm.coef);
     ctx->n_coef = m->n_coef;
     ctx->circ_pool_dev = nullptr;
@@ -212,5 +230,6 @@ extern "C" int rtb200_set_coeffs(rtb200_ctx* ctx, const double* coef_host, int64
     RT_CUDA(ctx, cudaMemcpy(ctx->coef_dev, coef_host, (size_t)n_coef * sizeof(double),
                             cudaMemcpyHostToDevice));
     ctx->pc_ready = false;
+    rt_sweep_invalidate(ctx);
     return RTB200_OK;
 }

@@ -9,8 +9,17 @@
 //            with ||v||^2 accumulated on the fly
 // followed by a scaling pass.  Reductions are two-stage (per-block partials,
 // then one block per output) so results are deterministic.  The small
-// Hessenberg least-squares problem (Givens rotations) runs on the host; one
-// stream synchronisation per iteration fetches k+3 doubles.
+// Hessenberg least-squares problem (Givens rotations) runs on the host, ONE ITERATION BEHIND
+// the device: the k+2 scalars of iteration k travel to pinned host memory with an
+// asynchronous copy + event, and the host reads them after it has enqueued iteration k+1,
+// so the stream never drains between iterations (a converged solve has enqueued one
+// Arnoldi step more than it uses).
+//
+// Preconditioning (rtb200_gmres_params.pc / pc_side): none; left (PETSc's KSPGMRES default,
+// residual norms of the preconditioned system); right and flexible (KSPFGMRES, which both
+// scatterer experiments of the reference select, solve.py:83 / input.json:4): the
+// z_k = M^-1 v_k are stored, x is updated with them and the residual norms are those of the
+// original system.
 #include "rtb200_internal.cuh"
 
 #include <algorithm>
@@ -21,7 +30,8 @@ namespace {
 
 constexpr int RED_BLOCKS_PER_SM = 4;
 constexpr int RED_THREADS = 256;
-constexpr int MAX_BASIS = 128;        // restart + 1 must not exceed this
+constexpr int MAX_BASIS = 1024;       // restart + 1 must not exceed this
+constexpr int RED_STRIDE = 68;        // doubles per block in the partial-sum buffer (<= 64 outputs per pass)
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -177,6 +187,7 @@ struct Work {
     double* h2;         // refinement dots
     double* nrm;        // [4] squared norms
     int* flag;
+    double* Z;          // m preconditioned basis vectors (flexible right preconditioning) or null
     int nblocks;
     int stride;
 };
@@ -260,15 +271,20 @@ struct Solver {
         return RTB200_OK;
     }
 
-    // y = A_ii x (optionally preconditioned from the left): w <- M^-1 A x
-    int op(const double* x, double* y, int pc) {
+    // w = M^-1 A v (left), w = A M^-1 v with z = M^-1 v kept in zk (right, flexible), or w = A v
+    int op(const double* v, double* w, int pc, int side, double* zk) {
         int rc;
-        if (pc) {
-            rc = rt_apply_with_halo(ctx, RTB200_TERM_ALL, 1, x, wk.t, st);
+        if (pc && side == 0) {
+            rc = rt_apply_with_halo(ctx, RTB200_TERM_ALL, 1, v, wk.t, st);
             if (rc) return rc;
-            return rt_pc_apply(ctx, wk.t, y, st);
+            return rt_pc_apply_type(ctx, pc, wk.t, w, st);
         }
-        return rt_apply_with_halo(ctx, RTB200_TERM_ALL, 1, x, y, st);
+        if (pc) {
+            rc = rt_pc_apply_type(ctx, pc, v, zk, st);
+            if (rc) return rc;
+            return rt_apply_with_halo(ctx, RTB200_TERM_ALL, 1, zk, w, st);
+        }
+        return rt_apply_with_halo(ctx, RTB200_TERM_ALL, 1, v, w, st);
     }
 };
 
@@ -315,14 +331,15 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
-extern "C" int64_t rtb200_gmres_work_bytes(const rtb200_ctx* ctx, int restart) {
+extern "C" int64_t rtb200_gmres_work_bytes(const rtb200_ctx* ctx, int restart, int pc_side) {
     if (!ctx || !ctx->have_mesh || restart < 1 || restart + 1 > MAX_BASIS) return -1;
     const size_t n = (size_t)ctx->dm.n_slab;
     const int nblocks = ctx->sm_count * RED_BLOCKS_PER_SM;
     size_t bytes = 0;
     bytes += align_up(sizeof(double) * n * (size_t)(restart + 1), 256);   // V
+    if (pc_side == 1) bytes += align_up(sizeof(double) * n * (size_t)restart, 256);   // Z
     bytes += align_up(sizeof(double) * n, 256) * 2;                        // w, t
-    bytes += align_up(sizeof(double) * (size_t)nblocks * (MAX_BASIS + 4), 256);
+    bytes += align_up(sizeof(double) * (size_t)nblocks * RED_STRIDE, 256);
     bytes += align_up(sizeof(double) * (MAX_BASIS + 4), 256) * 2;          // h, h2
     bytes += 256 * 2;                                                      // nrm, flag
     return (int64_t)bytes;
@@ -337,7 +354,11 @@ extern "C" int rtb200_gmres(rtb200_ctx* ctx, const double* b_dev, double* x_dev,
         return rt_fail(ctx, RTB200_EINVAL, "gmres: null argument");
     const int m = prm->restart;
     if (m < 1 || m + 1 > MAX_BASIS) return rt_fail(ctx, RTB200_EUNSUPPORTED, "gmres: restart out of range");
-    if (work_bytes < rtb200_gmres_work_bytes(ctx, m))
+    const int pc = prm->pc;
+    if (pc < RTB200_PC_NONE || pc > RTB200_PC_ELEMENT) return rt_fail(ctx, RTB200_EINVAL, "gmres: unknown preconditioner");
+    if (prm->pc_side != 0 && prm->pc_side != 1) return rt_fail(ctx, RTB200_EINVAL, "gmres: pc_side must be 0 or 1");
+    const int side = pc ? prm->pc_side : 0;
+    if (work_bytes < rtb200_gmres_work_bytes(ctx, m, side))
         return rt_fail(ctx, RTB200_EINVAL, "gmres: workspace too small");
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
 
@@ -350,8 +371,10 @@ extern "C" int rtb200_gmres(rtb200_ctx* ctx, const double* b_dev, double* x_dev,
     char* p = (char*)work_dev;
     Work& W = S.wk;
     W.nblocks = ctx->sm_count * RED_BLOCKS_PER_SM;
-    W.stride = MAX_BASIS + 4;
+    W.stride = RED_STRIDE;
     W.V = (double*)p; p += align_up(sizeof(double) * n * (size_t)(m + 1), 256);
+    W.Z = nullptr;
+    if (side == 1) { W.Z = (double*)p; p += align_up(sizeof(double) * n * (size_t)m, 256); }
     W.w = (double*)p; p += align_up(sizeof(double) * n, 256);
     W.t = (double*)p; p += align_up(sizeof(double) * n, 256);
     W.partial = (double*)p; p += align_up(sizeof(double) * (size_t)W.nblocks * W.stride, 256);
@@ -360,20 +383,30 @@ extern "C" int rtb200_gmres(rtb200_ctx* ctx, const double* b_dev, double* x_dev,
     W.nrm = (double*)p; p += 256;
     W.flag = (int*)p; p += 256;
 
-    const int pc = prm->pc;
-    if (pc) {
+    // pinned staging for the per-iteration scalars: two slots, the host runs one iteration behind
+    struct Pinned {
+        double* buf = nullptr;
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        ~Pinned() {
+            if (buf) cudaFreeHost(buf);
+            for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
+        }
+    } pin;
+    RT_CUDA(ctx, cudaMallocHost((void**)&pin.buf, sizeof(double) * 2 * (MAX_BASIS + 8)));
+    for (int i = 0; i < 2; ++i) RT_CUDA(ctx, cudaEventCreateWithFlags(&pin.ev[i], cudaEventDisableTiming));
+
+    if (pc == RTB200_PC_NODE) {
         int rc = rt_pc_setup(ctx, S.st);
         if (rc) return rc;
     }
-    const int64_t launches0 = ctx->launches;
     int64_t n_apply = 0;
     int rc;
-    double host[MAX_BASIS + 8];
+    double host[8];
 
     // ||b|| (preconditioned when a left preconditioner is used, like PETSc)
     const double* bb = b_dev;
-    if (pc) {
-        rc = rt_pc_apply(ctx, b_dev, W.t, S.st);
+    if (pc && side == 0) {
+        rc = rt_pc_apply_type(ctx, pc, b_dev, W.t, S.st);
         if (rc) return rc;
         bb = W.t;
     }
@@ -405,8 +438,8 @@ extern "C" int rtb200_gmres(rtb200_ctx* ctx, const double* b_dev, double* x_dev,
             k_sub<<<W.nblocks, RED_THREADS, 0, S.st>>>(b_dev, W.w, W.V, S.n2);
             ctx->launches++;
         }
-        if (pc) {
-            rc = rt_pc_apply(ctx, W.V, W.t, S.st);
+        if (pc && side == 0) {
+            rc = rt_pc_apply_type(ctx, pc, W.V, W.t, S.st);
             if (rc) return rc;
             RT_CUDA(ctx, cudaMemcpyAsync(W.V, W.t, sizeof(double) * n, cudaMemcpyDeviceToDevice, S.st));
         }
@@ -430,18 +463,16 @@ extern "C" int rtb200_gmres(rtb200_ctx* ctx, const double* b_dev, double* x_dev,
         std::fill(H.begin(), H.end(), 0.0);
         std::fill(Hraw.begin(), Hraw.end(), 0.0);
 
-        int k = 0;
-        for (; k < m && reason == 0; ++k) {
+        // device side of Arnoldi step k; its k + 2 scalars land in pinned slot k & 1
+        auto enqueue = [&](int k) -> int {
             double* vk1 = W.V + (size_t)(k + 1) * n;
-            rc = S.op(W.V + (size_t)k * n, W.w, pc);
-            if (rc) return rc;
+            int r2 = S.op(W.V + (size_t)k * n, W.w, pc, side, W.Z ? W.Z + (size_t)k * n : nullptr);
+            if (r2) return r2;
             n_apply++;
-            // h = V^T w, h[k+1] = ||w||^2
-            rc = S.mdot(W.V, k + 1, W.w, W.h);
-            if (rc) return rc;
-            // v_{k+1} = w - V h, nrm[0] = ||v||^2
-            rc = S.maxpy(W.V, k + 1, W.h, -1.0, W.w, vk1, W.nrm, nullptr);
-            if (rc) return rc;
+            r2 = S.mdot(W.V, k + 1, W.w, W.h);                        // h = V^T w, h[k+1] = ||w||^2
+            if (r2) return r2;
+            r2 = S.maxpy(W.V, k + 1, W.h, -1.0, W.w, vk1, W.nrm, nullptr);   // v_{k+1} = w - V h
+            if (r2) return r2;
             if (prm->orth != 2) {
                 // refinement pass (always, or when more than 1/sqrt(2) of w cancelled)
                 const int* flag = nullptr;
@@ -450,34 +481,39 @@ extern "C" int rtb200_gmres(rtb200_ctx* ctx, const double* b_dev, double* x_dev,
                     ctx->launches++;
                     flag = W.flag;
                 }
-                rc = S.mdot(W.V, k + 1, vk1, W.h2);
-                if (rc) return rc;
+                r2 = S.mdot(W.V, k + 1, vk1, W.h2);
+                if (r2) return r2;
                 k_maxpy<<<W.nblocks, RED_THREADS, 0, S.st>>>(W.V, S.n, k + 1, W.h2, -1.0, vk1, vk1,
                                                              S.n2, nullptr, flag);
                 k_add_h<<<1, 64, 0, S.st>>>(W.h, W.h2, k + 1, flag);
                 ctx->launches += 2;
-                rc = S.norm2(vk1, W.nrm);
-                if (rc) return rc;
+                r2 = S.norm2(vk1, W.nrm);
+                if (r2) return r2;
             }
             k_scale_inv_norm<<<W.nblocks, RED_THREADS, 0, S.st>>>(vk1, S.n2, W.nrm);
             ctx->launches++;
-            // fetch h[0..k] and the new norm
-            RT_CUDA(ctx, cudaMemcpyAsync(host, W.h, sizeof(double) * (k + 1), cudaMemcpyDeviceToHost, S.st));
-            rc = S.fetch(W.nrm, host + (k + 1), 1);
-            if (rc) return rc;
-            const double hk1 = std::sqrt(std::max(host[k + 1], 0.0));
+            double* slot = pin.buf + (size_t)(k & 1) * (MAX_BASIS + 8);
+            RT_CUDA(ctx, cudaMemcpyAsync(slot, W.h, sizeof(double) * (k + 1), cudaMemcpyDeviceToHost, S.st));
+            RT_CUDA(ctx, cudaMemcpyAsync(slot + (k + 1), W.nrm, sizeof(double), cudaMemcpyDeviceToHost, S.st));
+            RT_CUDA(ctx, cudaEventRecord(pin.ev[k & 1], S.st));
+            return RTB200_OK;
+        };
+        // host side of step k: Hessenberg column, rotations, convergence test
+        auto process = [&](int k) -> int {
+            RT_CUDA(ctx, cudaEventSynchronize(pin.ev[k & 1]));
+            const double* hk = pin.buf + (size_t)(k & 1) * (MAX_BASIS + 8);
+            const double hk1 = std::sqrt(std::max(hk[k + 1], 0.0));
             double* Hc = &H[(size_t)k * (m + 1)];
-            for (int i = 0; i <= k; ++i) Hc[i] = host[i];
+            for (int i = 0; i <= k; ++i) Hc[i] = hk[i];
             Hc[k + 1] = hk1;
             std::memcpy(&Hraw[(size_t)k * (m + 1)], Hc, sizeof(double) * (k + 2));
-            // previous rotations, then the new one
-            for (int i = 0; i < k; ++i) {
+            for (int i = 0; i < k; ++i) {                       // previous rotations, then the new one
                 const double a = cs[i] * Hc[i] + sn[i] * Hc[i + 1];
                 Hc[i + 1] = -sn[i] * Hc[i] + cs[i] * Hc[i + 1];
                 Hc[i] = a;
             }
             const double den = std::hypot(Hc[k], Hc[k + 1]);
-            if (den == 0.0) { reason = -5; ++k; break; }
+            if (den == 0.0) { reason = -5; return RTB200_OK; }  // column k is not used
             cs[k] = Hc[k] / den;
             sn[k] = Hc[k + 1] / den;
             Hc[k] = den;
@@ -486,16 +522,33 @@ extern "C" int rtb200_gmres(rtb200_ctx* ctx, const double* b_dev, double* x_dev,
             g[k] = cs[k] * g[k];
             resn = std::fabs(g[k + 1]);
             ++it;
+            last_cols = k + 1;
             if (hist && prm->record_history) hist[it] = resn;
             if (resn != resn) reason = -9;                       // NaN
             else if (resn <= ttol) reason = resn < prm->atol ? 3 : 2;
             else if (resn >= prm->divtol * res0) reason = -4;
             else if (it >= prm->max_it) reason = -3;
             else if (hk1 == 0.0) reason = -5;                    // happy breakdown without convergence
+            return RTB200_OK;
+        };
+
+        last_cols = 0;
+        int enq = 0;                                             // steps enqueued in this cycle
+        for (int k = 0; k < m && reason == 0; ++k) {
+            rc = enqueue(k);
+            if (rc) return rc;
+            enq = k + 1;
+            if (k >= 1) {
+                rc = process(k - 1);
+                if (rc) return rc;
+            }
         }
-        // k columns are valid: solve the triangular system and update x
-        const int kc = k;
-        last_cols = kc;
+        if (reason == 0 && enq > 0) {
+            rc = process(enq - 1);
+            if (rc) return rc;
+        }
+        // last_cols columns are valid: solve the triangular system and update x
+        const int kc = last_cols;
         for (int i = kc - 1; i >= 0; --i) {
             double s = g[i];
             for (int j = i + 1; j < kc; ++j) s -= H[(size_t)j * (m + 1) + i] * yv[j];
@@ -503,9 +556,11 @@ extern "C" int rtb200_gmres(rtb200_ctx* ctx, const double* b_dev, double* x_dev,
         }
         if (kc > 0) {
             RT_CUDA(ctx, cudaMemcpyAsync(W.h, yv.data(), sizeof(double) * kc, cudaMemcpyHostToDevice, S.st));
-            rc = S.maxpy(W.V, kc, W.h, +1.0, x_dev, x_dev, nullptr, nullptr);
+            rc = S.maxpy(W.Z ? W.Z : W.V, kc, W.h, +1.0, x_dev, x_dev, nullptr, nullptr);
             if (rc) return rc;
             RT_CUDA(ctx, cudaStreamSynchronize(S.st));    // yv is reused by the next cycle
+        } else if (reason == 0) {
+            reason = -5;                                  // no usable direction: do not spin
         }
     }
 
@@ -534,6 +589,5 @@ extern "C" int rtb200_gmres(rtb200_ctx* ctx, const double* b_dev, double* x_dev,
                 Hs[(size_t)j * (last_cols + 1) + i] = Hraw[(size_t)j * (m + 1) + i];
         extreme_singular_values(Hs, last_cols + 1, last_cols, &res->sigma_max, &res->sigma_min);
     }
-    (void)launches0;
     return RTB200_OK;
 }

@@ -268,6 +268,13 @@ int rt_pc_apply(rtb200_ctx* ctx, const double* x, double* y, cudaStream_t st) {
     return RTB200_OK;
 }
 
+// dispatch on the preconditioner kind (rtb200_gmres_params.pc / rtb200_pc_set_type)
+int rt_pc_apply_type(rtb200_ctx* ctx, int pc_type, const double* x, double* y, cudaStream_t st) {
+    if (pc_type == RTB200_PC_NODE) return rt_pc_apply(ctx, x, y, st);
+    if (pc_type == RTB200_PC_SWEEP || pc_type == RTB200_PC_ELEMENT) return rt_sweep_apply(ctx, pc_type, x, y, st);
+    return rt_fail(ctx, RTB200_EINVAL, "unknown preconditioner kind");
+}
+
 void rt_pc_destroy(rtb200_ctx* ctx) {
     ctx->pc_ready = false;
     ctx->pc_eig_pool = nullptr;        // freed with the other tables (ctx->allocs)
@@ -311,5 +318,5 @@ extern "C" int rtb200_pc_apply(rtb200_ctx* ctx, const double* x_slab_dev, double
     if (!ctx->have_mesh) return rt_fail(ctx, RTB200_ESTATE, "no mesh set (call rtb200_set_mesh first)");
     if (!x_slab_dev || !y_slab_dev) return rt_fail(ctx, RTB200_EINVAL, "null device vector");
     if (x_slab_dev == y_slab_dev) return rt_fail(ctx, RTB200_EINVAL, "pc_apply: x and y must not alias");
-    return rt_pc_apply(ctx, x_slab_dev, y_slab_dev, (cudaStream_t)stream);
+    return rt_pc_apply_type(ctx, ctx->pc_type, x_slab_dev, y_slab_dev, (cudaStream_t)stream);
 }

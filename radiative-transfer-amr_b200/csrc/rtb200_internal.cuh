@@ -27,6 +27,7 @@ struct DevMesh {
     const double *g_pool, *exy_pool, *eth_pool;
     const int32_t* acpl_pool;
     const double* coef;
+    const int32_t* face_nbr;
 };
 
 // A launch bucket: columns with nx == ny == n (n = 0: anything else).
@@ -87,6 +88,15 @@ struct rtb200_ctx {
     int64_t* pc_eig_off = nullptr; // [n_sig] device copy
     std::vector<int64_t> pc_eig_off_host;
 
+    // transport-sweep / element block-Jacobi preconditioner state (precond_sweep.cu)
+    int pc_type = RTB200_PC_NODE;  // what rtb200_pc_apply computes
+    int pc_ncorr = -1;             // defect-correction steps of the local solves (-1: choose from the data)
+    struct SweepState* sweep = nullptr;
+    // host copies of the tables the sweep schedule is built from (rtb200_set_mesh)
+    std::vector<int32_t> h_col_nx, h_col_ny, h_col_sig, h_col_bdry, h_face_nbr, h_sig_nt, h_th_bits;
+    std::vector<int64_t> h_sig_th0, h_col_coef_off;
+    std::vector<double> h_col_dx, h_col_dy, h_lgl_w, h_lgl_s;
+
     // halo / multi-GPU
     int rank = 0, nranks = 1;
     void* nccl_comm = nullptr;
@@ -120,4 +130,9 @@ void rt_comm_destroy(rtb200_ctx* ctx);
 // precond_circ.cuh / precond_eig.cuh (compiled into apply.cu)
 int rt_pc_setup(rtb200_ctx* ctx, cudaStream_t st);
 int rt_pc_apply(rtb200_ctx* ctx, const double* x, double* y, cudaStream_t st);
+int rt_pc_apply_type(rtb200_ctx* ctx, int pc_type, const double* x, double* y, cudaStream_t st);
 void rt_pc_destroy(rtb200_ctx* ctx);
+// precond_sweep.cu
+int rt_sweep_apply(rtb200_ctx* ctx, int pc_type, const double* r, double* z, cudaStream_t st);
+void rt_sweep_destroy(rtb200_ctx* ctx);
+void rt_sweep_invalidate(rtb200_ctx* ctx);      // coefficients changed

@@ -206,6 +206,23 @@ class MeshArrays:
                           np.zeros(nc, np.int32), nbr, [s])
 
 
+_LGL_TABLES = None
+
+
+def _lgl_tables():
+    """(lgl_w[(MAX_NXY + 1), MAX_NXY], lgl_s[(MAX_NXY + 1), MAX_NXY, MAX_NXY]) for all orders."""
+    global _LGL_TABLES
+    if _LGL_TABLES is None:
+        from ..rt import tables as T
+        w = np.zeros((MAX_NXY + 1, MAX_NXY))
+        s = np.zeros((MAX_NXY + 1, MAX_NXY, MAX_NXY))
+        for n in range(1, MAX_NXY + 1):
+            w[n, :n] = lgl_rule(n)[1]
+            s[n, :n, :n] = T.stiffness(n)
+        _LGL_TABLES = (w, s)
+    return _LGL_TABLES
+
+
 def _along(F: int) -> int:
     """Coordinate that runs along face F: y (1) for x-faces, x (0) for y-faces."""
     return 1 if F % 2 == 0 else 0
@@ -318,9 +335,9 @@ class FlatMesh:
         # ---- spatial tables per n ------------------------------------------ #
         self.lgl_w = np.zeros((MAX_NXY + 1, MAX_NXY))
         self.lgl_s = np.zeros((MAX_NXY + 1, MAX_NXY, MAX_NXY))
-        for n in sorted(set(A.nx.tolist()) | set(A.ny.tolist())):
-            self.lgl_w[n, :n] = lgl_rule(n)[1]
-            self.lgl_s[n, :n, :n] = T.stiffness(n)
+        # every order 1..MAX_NXY, not only the ones of this mesh: the library keeps these tables
+        # in process-global __constant__ memory, so they must be identical for every context
+        self.lgl_w[:], self.lgl_s[:] = _lgl_tables()
 
         # ---- faces: neighbour traces, spatial and angular mortars ---------- #
         self.face_base = -np.ones(nc * 8, np.int64)
@@ -328,6 +345,9 @@ class FlatMesh:
         self.face_exy = np.zeros(nc * 8, np.int32)
         self.face_n1 = np.zeros(nc * 8, np.int32)
         self.face_acpl = np.zeros(nc * 8, np.int32)
+        # local index of the neighbour column (-1 none, -2 other rank, -3 periodic wrap-around):
+        # the upwind ordering of the transport-sweep preconditioner is built from it
+        self.face_nbr = -np.ones(nc * 8, np.int32)
         exy_pool, exy_ids = [], {}
 
         def exy_pool_view(off, n1_, n0_):
@@ -374,6 +394,11 @@ class FlatMesh:
                 self.face_n1[fidx] = n1
                 local = owner[g1] == self.rank
                 self.face_base[fidx[local]] = slab_off_of[g1[local]] + (row0 * ntp1)[local]
+                # geometrically adjacent?  (a periodic wrap-around neighbour is not)
+                mine_edge = pos[g0, {0: 2, 1: 3, 2: 0, 3: 1}[F]]
+                their_edge = pos[g1, {0: 0, 1: 1, 2: 2, 3: 3}[F]]
+                adjacent = np.abs(mine_edge - their_edge) <= 1e-12 * max(A.Ls)
+                self.face_nbr[fidx] = np.where(~local, -2, np.where(adjacent, g1 - self.c0, -3))
                 # ghost traces are packed [n1][ntp1] rows
                 for t in np.flatnonzero(~local):
                     gid = (int(owner[g1[t]]), int(g1[t]), (F + 2) % 4)

@@ -125,6 +125,7 @@ class Projection:
     def from_vector(self, vec: np.ndarray):
         """Inverse of :meth:`to_vector` (``from_vector.py:11-40``)."""
         vec = np.asarray(vec)
+        self._device = None            # a device copy left by Problem.solve is stale now
         g = 0
         for col_key, col in sorted(self.mesh.cols.items()):
             assert col.is_lf
@@ -137,6 +138,17 @@ class Projection:
                     np.array(vec[g:g + n], dtype=np.float64).reshape(nx, ny, nth)
                 g += n
         return self
+
+    def checksum(self) -> tuple:
+        """(sum, sum of squares) of all nodal values: detects a projection whose values were
+        edited after its device copy was made (rt_b200.amr.device_solution)."""
+        s1 = s2 = 0.0
+        for _, col in sorted(self.cols.items()):
+            for _, cell in sorted(col.cells.items()):
+                v = np.asarray(cell.vals, dtype=np.float64)
+                s1 += float(v.sum())
+                s2 += float(np.vdot(v, v))
+        return (s1, s2)
 
     def cell_intg_xy(self, col_key: int, cell_key: int) -> np.ndarray:
         """Spatial integral of one cell per angular node, ``[nth]``

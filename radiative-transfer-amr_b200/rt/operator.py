@@ -27,6 +27,7 @@ from ..dg.quadrature import lgl_rule
 from ..dg.projection import push_forward
 from . import tables as T
 
+PC_KINDS = {"none": L.PC_NONE, "node": L.PC_NODE, "sweep": L.PC_SWEEP, "element": L.PC_ELEMENT}
 TERMS = {"mass": L.TERM_MASS, "scat": L.TERM_SCAT, "iconv": L.TERM_ICONV,
          "bconv": L.TERM_BCONV, "all": L.TERM_ALL}
 
@@ -197,7 +198,7 @@ class RTOperator:
         m.n_col, m.n_sig, m.n_sigcell = f.n_col, f.n_sig, f.n_sigcell
         m.n_dof, m.n_slab, m.n_ghost = f.n_dof, f.n_slab, f.n_ghost
         for name in ("col_nx", "col_ny", "col_sig", "col_bdry", "face_rstride", "face_exy",
-                     "face_n1", "face_acpl", "sig_nt", "sig_ntp", "sig_ncell", "sig_cell0",
+                     "face_n1", "face_acpl", "face_nbr", "sig_nt", "sig_ntp", "sig_ncell", "sig_cell0",
                      "cell_nth", "cell_thoff", "th_cell", "th_bits"):
             put(name, getattr(f, name), np.int32, C.c_int32)
         for name in ("col_dof_off", "col_slab_off", "col_coef_off", "face_base", "sig_th0"):
@@ -229,6 +230,11 @@ class RTOperator:
             self._call("rtb200_pc_set_eig", self.lib.rtb200_pc_set_eig(
                 self.ctx, _as_c(off, C.c_int64), C.c_int32(off.size), _as_c(pool, C.c_double),
                 C.c_int64(pool.size)))
+        # 1-D fast-diagonalisation tables of the transport-sweep preconditioner
+        fd_off, fd_pool = T.fd_tables(L.MAX_NXY)
+        self._call("rtb200_pc_set_fd", self.lib.rtb200_pc_set_fd(
+            self.ctx, _as_c(fd_off, C.c_int64), C.c_int32(fd_off.size), _as_c(fd_pool, C.c_double),
+            C.c_int64(fd_pool.size)))
 
     def _call(self, what, rc):
         L.check(self.lib, self.ctx, rc, what)
@@ -316,11 +322,25 @@ class RTOperator:
             return y
         return yd
 
+    def pc_set_type(self, kind="node", n_corr: int = -1):
+        """What ``pc_apply`` computes: 'node' (node-wise (M - S)^-1), 'sweep' (transport sweep,
+        (M + BC - IC)^-1 with the column mid-range extinction + ``n_corr`` local defect
+        corrections, -1 = chosen from the data) or 'element' (its block-diagonal part)."""
+        self._call("rtb200_pc_set_type", self.lib.rtb200_pc_set_type(
+            self.ctx, int(PC_KINDS.get(kind, kind)), int(n_corr)))
+
+    def pc_sweep_info(self) -> dict:
+        """Levels (= launches per sweep) and (column, quadrant) elements of the upwind schedule."""
+        nl, ni = C.c_int32(), C.c_int64()
+        self._call("rtb200_pc_sweep_info", self.lib.rtb200_pc_sweep_info(
+            self.ctx, C.byref(nl), C.byref(ni)))
+        return {"levels": int(nl.value), "elements": int(ni.value)}
+
     def pc_apply(self, r_slab, z_slab=None):
-        """z = mask . (M - S)^{-1} r on slab-order device tensors: the node-wise
-        block-Jacobi preconditioner (inverse of the reference's ``preconditioner_matrix``):
-        block-circulant FFT on uniform angular meshes, per-signature eigen tables otherwise
-        (symmetric scattering kernels)."""
+        """z = M^-1 r on slab-order device tensors with the preconditioner chosen by
+        ``pc_set_type`` (default: node-wise block-Jacobi, the inverse of the reference's
+        ``preconditioner_matrix``: block-circulant FFT on uniform angular meshes,
+        per-signature eigen tables otherwise)."""
         z_slab = self.empty_slab() if z_slab is None else z_slab
         self._call("rtb200_pc_apply", self.lib.rtb200_pc_apply(
             self.ctx, C.c_void_p(r_slab.data_ptr()), C.c_void_p(z_slab.data_ptr()), self._stream()))
@@ -345,22 +365,27 @@ class RTOperator:
 
     # ------------------------------------------------------------------ #
     def gmres(self, b_slab, x_slab, restart: int = 50, max_it: int = 5000, rtol: float = 1e-15,
-              atol: float = 1e-15, divtol: float = None, orth: int = 0, pc: int = 0,
-              x0_nonzero: bool = True, record_history: bool = True):
+              atol: float = 1e-15, divtol: float = None, orth: int = 0, pc=0,
+              x0_nonzero: bool = True, record_history: bool = True, flexible: bool = False):
         """Solve A_ii x = b on slab-order device tensors; x is updated in place.
-        Returns the info dict (PETSc-style reason code, history, ...)."""
+        ``pc``: 0 / 'none', 1 / 'node', 2 / 'sweep', 3 / 'element' (``PC_KINDS``);
+        ``flexible``: right-preconditioned flexible GMRES (PETSc's fgmres) instead of the
+        left-preconditioned default.  Returns the info dict (PETSc-style reason code,
+        history, ...)."""
+        pc = int(PC_KINDS.get(pc, pc))
+        side = 1 if (flexible and pc) else 0
         torch = _torch()
         if divtol is None:
             divtol = float(np.sqrt(np.finfo(np.float64).max))
-        nbytes = int(self.lib.rtb200_gmres_work_bytes(self.ctx, int(restart)))
+        nbytes = int(self.lib.rtb200_gmres_work_bytes(self.ctx, int(restart), side))
         if nbytes < 0:
             raise L.RTB200Error("gmres: unsupported restart %d" % restart)
-        if self._work is None or self._work_restart != restart or self._work.numel() < nbytes:
+        if self._work is None or self._work.numel() < nbytes:
             self._work = None
             self._work = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            self._work_restart = restart
         prm = L.GmresParams(int(restart), int(max_it), float(rtol), float(atol), float(divtol),
-                            int(orth), int(pc), int(bool(x0_nonzero)), int(bool(record_history)))
+                            int(orth), int(pc), int(bool(x0_nonzero)), int(bool(record_history)),
+                            side)
         res = L.GmresResult()
         hist = np.zeros(int(max_it) + 2)
         self._call("rtb200_gmres", self.lib.rtb200_gmres(

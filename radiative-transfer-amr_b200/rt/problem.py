@@ -50,6 +50,41 @@ def _eval_nodal(fn, X, Y, Th):
     return out
 
 
+def _rank_size(kwargs):
+    """(rank, nranks) of the column partition: explicit keyword arguments, else the
+    torch.distributed process group when one is initialised (one process per GPU, like the
+    reference's one MPI rank per process, ``mass_matrix.py:44-51``), else (0, 1)."""
+    if "nranks" in kwargs or "rank" in kwargs:
+        return int(kwargs.get("rank", 0)), int(kwargs.get("nranks", 1))
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return 0, 1
+
+
+def _mesh_fingerprint(mesh):
+    """Cheap structural hash of a mesh: leaves, orders and angular cells."""
+    if isinstance(mesh, FlatMesh):
+        return ("flat", mesh.n_dof_global, mesh.n_col)
+    h = 0
+    for ck, col in mesh.cols.items():
+        h = hash((h, ck, tuple(col.ndofs), tuple((k, c.ndofs[0]) for k, c in col.cells.items())))
+    return h
+
+
+# pc_type keyword of Problem.solve -> preconditioner of the library.  PETSc's own "bjacobi"
+# (rank-block ILU(0), the reference default, solve.py:24,93-95) and "kaczmarz" (scatterer
+# experiments, input.json:5) cannot be reproduced (their arithmetic lives in PETSc); both
+# are served by the transport sweep, which is what an ILU(0) of the upwind-ordered operator
+# amounts to.  The library's own kinds can be named directly.
+PC_OF_TYPE = {None: "none", "none": "none", "bjacobi": "sweep", "kaczmarz": "sweep", "ilu": "sweep",
+              "sweep": "sweep", "node_bjacobi": "node", "node": "node",
+              "element_bjacobi": "element", "element": "element"}
+
+
 class TermOperator:
     """``sign * (selected terms of A)`` with a PETSc-``Mat``-like ``mult``."""
 
@@ -87,15 +122,19 @@ class Problem:
 
     # ---- operator construction ("element-matrix assembly") -------------- #
     def operator(self, mesh, **kwargs) -> RTOperator:
-        """Device operator for ``mesh``; rebuilt when the mesh object changes."""
-        rank, nranks = kwargs.get("rank", 0), kwargs.get("nranks", 1)
-        if self._op_cache is not None:
-            key, op = self._op_cache
-            if key[0] is mesh and key[1:] == (rank, nranks) and key[0].get_ndof() == op.flat.n_dof_global:
-                return op
-            op.close()
+        """Device operator for ``mesh``; rebuilt when the mesh (object or structure: leaves,
+        orders), the partition or one of the coefficient callables changes.  A replaced
+        operator is not closed here -- ``TermOperator``s handed out earlier may still use it;
+        its context is released when the last reference goes away."""
+        rank, nranks = _rank_size(kwargs)
+        key = (id(mesh), rank, nranks, id(self.kappa), id(self.sigma), id(self.Phi),
+               _mesh_fingerprint(mesh))
+        if self._op_cache is not None and self._op_cache[0] == key:
+            return self._op_cache[1]
         op = RTOperator(mesh, self.kappa, self.sigma, self.Phi, rank=rank, nranks=nranks)
-        self._op_cache = ((mesh, rank, nranks), op)
+        if nranks > 1:
+            op.comm_init(rank, nranks)
+        self._op_cache = (key, op, mesh)        # the mesh reference keeps id(mesh) unique
         return op
 
     def mass_matrix(self, mesh, **kwargs):
@@ -209,17 +248,22 @@ class Problem:
         opts = {"verbose": False, "ksp_type": "gmres", "pc_type": "bjacobi", **kwargs}
         if opts["ksp_type"] not in ("gmres", "fgmres"):
             raise ValueError("unsupported ksp_type %r (gmres, fgmres)" % opts["ksp_type"])
+        if opts["pc_type"] not in PC_OF_TYPE:
+            raise ValueError("unsupported pc_type %r (%s)" % (opts["pc_type"], sorted(map(str, PC_OF_TYPE))))
+        rank, nranks = _rank_size(kwargs)
         t0 = perf_counter()
-        op = self.operator(mesh, **{k: v for k, v in kwargs.items() if k in ("rank", "nranks")})
+        op = self.operator(mesh, **kwargs)
         t_tables = perf_counter() - t0
 
+        # global right-hand sides (host, like the reference), this rank's block of them
         f_vec = self.forcing_vector(mesh, **kwargs)
         g_vec = self.boundary_conditions_vector(mesh, **kwargs)
         t_rhs = perf_counter() - t0 - t_tables
+        lo, hi = op.flat.dof0, op.flat.dof0 + op.flat.n_dof
 
         # interior / inflow-boundary split on the device (split_vector.py:15-48)
-        f_i = op.mask_slab(op.to_slab(f_vec), "interior")
-        g_b = op.mask_slab(op.to_slab(g_vec), "boundary")
+        f_i = op.mask_slab(op.to_slab(np.ascontiguousarray(f_vec[lo:hi])), "interior")
+        g_b = op.mask_slab(op.to_slab(np.ascontiguousarray(g_vec[lo:hi])), "boundary")
         # rhs = f_i - A_ib g_b  (solve.py:67-69)
         rhs = f_i - op.apply_slab(g_b, None, L.TERM_ALL, True)
         x = f_i.clone()                                   # initial guess = forcing (solve.py:72)
@@ -229,23 +273,20 @@ class Problem:
         divtol = float(np.sqrt(consts.INF))
         max_it = int(opts.get("max_it", 5000))
         restart = int(opts.get("restart", 50))
-        # Any preconditioner request (the reference's "bjacobi" default, "kaczmarz" of the
-        # scatterer experiments, input.json:4-5) is served by the node-wise block-Jacobi
-        # preconditioner of the library -- PETSc's own PCs are not available here; converged
-        # solutions do not depend on the choice.  "none" switches it off; when the library has
-        # no tables for the mesh (non-symmetric scattering kernel on an hp angular mesh) the
-        # solve runs unpreconditioned and says so in matrix_info["pc_type_used"].
         pc_type = opts["pc_type"]
-        pc = 0 if pc_type in (None, "none") else 1
+        pc_kind = PC_OF_TYPE[pc_type]
+        flexible = opts["ksp_type"] == "fgmres"
         t1 = perf_counter()
         gm = dict(restart=restart, max_it=max_it, rtol=rtol, atol=atol, divtol=divtol,
-                  orth=int(opts.get("orth", 0)), x0_nonzero=True)
+                  orth=int(opts.get("orth", 0)), x0_nonzero=True, flexible=flexible)
+        if "pc_corrections" in opts:
+            op.pc_set_type("sweep" if pc_kind == "none" else pc_kind, int(opts["pc_corrections"]))
         try:
-            info = op.gmres(rhs, x, pc=pc, **gm)
+            info = op.gmres(rhs, x, pc=pc_kind, **gm)
         except L.RTB200Error as exc:
-            if not (pc and "code -4" in str(exc)):   # RTB200_EUNSUPPORTED from the preconditioner
+            if not (pc_kind != "none" and "code -4" in str(exc)):   # RTB200_EUNSUPPORTED from the PC
                 raise
-            pc = 0
+            pc_kind = "none"
             x.copy_(f_i)
             info = op.gmres(rhs, x, pc=0, **gm)
         import torch
@@ -253,11 +294,19 @@ class Problem:
         t_solve = perf_counter() - t1
 
         u_slab = x + g_b                                  # merge_vectors.py:14-56
-        uh_vec = op.from_slab(u_slab).cpu().numpy()
-        uh_proj = Projection(mesh).from_vector(uh_vec)
+        uh_loc = op.from_slab(u_slab).cpu().numpy()
+        if nranks > 1:                                    # gather to every rank (root needs it)
+            import torch.distributed as dist
+            parts = [None] * nranks
+            dist.all_gather_object(parts, (int(lo), uh_loc))
+            uh_vec = np.concatenate([p[1] for p in sorted(parts, key=lambda p: p[0])])
+        else:
+            uh_vec = uh_loc
+        uh_proj = Projection(mesh).from_vector(uh_vec) if rank == 0 else None   # solve.py:132-136
         # the solution stays on the device for the error indicators of the AMR loop
-        # (rt_b200.amr.Error_Indicator reads it in place)
-        uh_proj._device = (op, u_slab)
+        # (rt_b200.amr.Error_Indicator reads it in place; single rank)
+        if uh_proj is not None and nranks == 1:
+            uh_proj._device = (op, u_slab, uh_proj.checksum())
 
         hist = info["history"]
         convergence_info = {"converged_reason": info["reason"],
@@ -271,7 +320,7 @@ class Problem:
                        "layout": op.flat.stats(), "true_residual_norm": info["true_res_norm"],
                        "operator_applies": info["n_apply"],
                        "ksp_type": opts["ksp_type"], "pc_type_requested": pc_type,
-                       "pc_type_used": "node_bjacobi" if pc else "none",
+                       "pc_type_used": pc_kind, "ranks": nranks,
                        "time_tables_s": t_tables, "time_rhs_s": t_rhs, "time_solve_s": t_solve}
         if opts["verbose"]:
             cond = info["sigma_max"] / info["sigma_min"] if info["sigma_min"] else consts.INF

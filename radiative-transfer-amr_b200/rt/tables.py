@@ -160,6 +160,54 @@ def pc_eig_tables(G: np.ndarray, wt: np.ndarray, rtol: float = 1.0e-12):
 
 
 # --------------------------------------------------------------------------- #
+# transport-sweep preconditioner: 1-D fast-diagonalisation tables
+# --------------------------------------------------------------------------- #
+def upwind_operator_1d(n: int, sign: int, masked: bool) -> np.ndarray:
+    """W^-1 B for the n-point LGL basis: B = -S + (outflow end node), the 1-D factor of
+    the (column, angle) diagonal block of M + BC - IC (``interior_convection_matrix.py:
+    179-237`` volume term, ``boundary_convection_matrix.py:303-338`` outflow faces) for a
+    flow in the +xi (``sign`` > 0: outflow through the last node) or -xi direction.
+    ``masked``: the inflow end node is an inflow-boundary node (``get_masks.py:80-110``),
+    i.e. not an unknown: its row and column are replaced by a decoupled 1 x 1 block."""
+    _, w = lgl_rule(n)
+    w = np.asarray(w, dtype=np.float64)
+    B = -stiffness(n)
+    if sign > 0:
+        B[n - 1, n - 1] += 1.0
+        m = 0
+    else:
+        B[0, 0] -= 1.0
+        m = n - 1
+    A = B / w[:, None]
+    if masked:
+        A[m, :] = 0.0
+        A[:, m] = 0.0
+        A[m, m] = 1.0 if sign > 0 else -1.0
+    return A
+
+
+def fd_tables(max_n: int = 12):
+    """Tables of ``rtb200_pc_set_fd``: for n = 1..max_n and variant
+    v = (sign < 0) + 2 * masked the eigen-decomposition W^-1 B = V diag(lam) V^-1 of
+    ``upwind_operator_1d`` as [lam: n][V: n x n][L = V^-1 W^-1: n x n], complex (re, im).
+    Returns (off int64[(max_n + 1) * 4] (-1: none), pool float64)."""
+    off = -np.ones((max_n + 1) * 4, np.int64)
+    parts, pos = [], 0
+    for n in range(1, max_n + 1):
+        _, w = lgl_rule(n)
+        Winv = np.diag(1.0 / np.asarray(w, dtype=np.float64))
+        for v in range(4):
+            A = upwind_operator_1d(n, -1 if (v & 1) else +1, bool(v & 2))
+            lam, V = np.linalg.eig(A)
+            L = np.linalg.solve(V, Winv.astype(np.complex128))
+            tab = np.concatenate([lam, V.reshape(-1), L.reshape(-1)]).astype(np.complex128)
+            off[n * 4 + v] = pos
+            parts.append(tab.view(np.float64))
+            pos += 2 * tab.size
+    return off, np.concatenate(parts)
+
+
+# --------------------------------------------------------------------------- #
 # block-circulant scattering (uniform angular meshes)
 # --------------------------------------------------------------------------- #
 def circulant_blocks(G: np.ndarray, nc: int, p: int, rtol: float = 1.0e-13):

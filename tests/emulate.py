@@ -263,3 +263,147 @@ def pc_eig_emulated(flat, coef, eig_off, eig_pool, shift, r_slab):
             t = (r @ W) / (mk - ms * lam)
             z[off + n * ntp: off + n * ntp + nt] = t @ Wt
     return z
+
+
+# --------------------------------------------------------------------------- #
+# transport-sweep preconditioner (csrc/precond_sweep.cu)
+# --------------------------------------------------------------------------- #
+def _quadrant_of_bits(bits):
+    return {3: 0, 6: 1, 12: 2, 9: 3}[bits & 15]
+
+
+def sweep_levels(flat):
+    """Topological levels of the (column, quadrant) elements, as build_schedule does."""
+    nc = flat.n_col
+    deps = {}
+    for c in range(nc):
+        for q in range(4):
+            d = []
+            for F in ((q + 2) & 3, (q + 3) & 3):
+                for slot in range(2):
+                    nb = int(flat.face_nbr[c * 8 + F * 2 + slot])
+                    if nb >= 0:
+                        d.append(nb * 4 + q)
+            deps[c * 4 + q] = d
+    level = {}
+    remaining = set(deps)
+    levels = []
+    while remaining:
+        cur = sorted(i for i in remaining if all(d in level for d in deps[i]))
+        assert cur, "cycle in the upwind graph"
+        for i in cur:
+            level[i] = len(levels)
+        levels.append(cur)
+        remaining -= set(cur)
+    return levels
+
+
+def fd_solve(fd, nx, ny, vx, vy, kbwt, ax, ay, b):
+    """numpy twin of fd_solve<>: b[nx, ny] -> z[nx, ny]."""
+    off, pool = fd
+
+    def tab(n, v):
+        p = pool[off[n * 4 + v]: off[n * 4 + v] + 2 * (n + 2 * n * n)].view(np.complex128)
+        return p[:n], p[n:n + n * n].reshape(n, n), p[n + n * n:].reshape(n, n)
+
+    lx, Vx, Lx = tab(nx, vx)
+    ly, Vy, Ly = tab(ny, vy)
+    t = Lx @ b @ Ly.T
+    t = t / (kbwt + ax * lx[:, None] + ay * ly[None, :])
+    return (Vx @ t @ Vy.T).real
+
+
+def sweep_pc(flat, coef, fd, r, couple=True, ncorr=0):
+    """numpy transliteration of k_pc_sweep over all levels: z = mask . T~^{-1} r."""
+    f = flat
+    z = np.zeros_like(r)
+    MAXN = f.lgl_w.shape[1]
+    levels = sweep_levels(f) if couple else [[c * 4 + q for c in range(f.n_col) for q in range(4)]]
+    for lvl in levels:
+        for item in lvl:
+            c, q = item >> 2, item & 3
+            nx, ny = int(f.col_nx[c]), int(f.col_ny[c])
+            nn = nx * ny
+            sg = int(f.col_sig[c])
+            nt, ntp = int(f.sig_nt[sg]), int(f.sig_ntp[sg])
+            soff, tp0 = int(f.col_slab_off[c]), int(f.sig_th0[sg])
+            hdx, hdy = 0.5 * f.col_dx[c], 0.5 * f.col_dy[c]
+            bdry = int(f.col_bdry[c])
+            mk = coef[f.col_coef_off[c]: f.col_coef_off[c] + nn].reshape(nx, ny)
+            wx, wy = f.lgl_w[nx][:nx], f.lgl_w[ny][:ny]
+            Sx, Sy = f.lgl_s[nx][:nx, :nx], f.lgl_s[ny][:ny, :ny]
+            kap = mk / (hdx * hdy * wx[:, None] * wy[None, :])
+            kbar = hdx * hdy * 0.5 * (max(kap.max(), 0.0) + max(kap.min(), 0.0))
+            for th in range(nt):
+                bits = int(f.th_bits[tp0 + th])
+                if _quadrant_of_bits(bits) != q:
+                    continue
+                wt, ct, sn = f.th_wt[tp0 + th], f.th_ct[tp0 + th], f.th_st[tp0 + th]
+                ox_hi, oy_hi = bool(bits & 1), bool(bits & 2)
+                Fx, Fy = (2 if ox_hi else 0), (3 if oy_hi else 1)
+                mx, my = bool((bdry >> Fx) & 1), bool((bdry >> Fy) & 1)
+                imx, jmy = (0 if ox_hi else nx - 1), (0 if oy_hi else ny - 1)
+                b = r[soff + np.arange(nn) * ntp + th].reshape(nx, ny).copy()
+                if couple:
+                    cell = int(f.th_cell[tp0 + th])
+                    rr = (bits >> 8) & 0xff
+                    nth0 = int(f.cell_nth[f.sig_cell0[sg] + cell])
+                    for F in (Fx, Fy):
+                        if (bdry >> F) & 1:
+                            continue
+                        n0 = nx if F & 1 else ny
+                        half = hdx if F & 1 else hdy
+                        wq = wx if F & 1 else wy
+                        wFF = f.th_wF[F, tp0 + th]
+                        fa = np.zeros(MAXN)
+                        for slot in range(2):
+                            fidx = c * 8 + F * 2 + slot
+                            if int(f.face_nbr[fidx]) < 0:
+                                continue
+                            b0 = int(f.face_base[fidx])
+                            rs, n1 = int(f.face_rstride[fidx]), int(f.face_n1[fidx])
+                            eo, ao = int(f.face_exy[fidx]), int(f.face_acpl[fidx])
+                            if eo < 0 and ao < 0:
+                                for p in range(n0):
+                                    fa[p] = half * wFF * wq[p] * z[b0 + p * rs + th]
+                                continue
+                            for j1 in range(n1):
+                                if ao < 0:
+                                    tmp = wFF * z[b0 + j1 * rs + th]
+                                else:
+                                    acp = f.acpl_pool[ao + cell * 6: ao + cell * 6 + 6]
+                                    tmp = 0.0
+                                    for k in range(2):
+                                        e1, t1, n1t = int(acp[k * 3]), int(acp[k * 3 + 1]), int(acp[k * 3 + 2])
+                                        for a in range(n1t):
+                                            tmp += f.eth_pool[e1 + a * nth0 + rr] * z[b0 + j1 * rs + t1 + a]
+                                tmp *= half
+                                if eo < 0:
+                                    fa[j1] += wq[j1] * tmp
+                                else:
+                                    E = f.exy_pool[eo: eo + n1 * n0].reshape(n1, n0)
+                                    fa[:n0] += E[j1, :] * tmp
+                        if F & 1:
+                            b[:, jmy] -= fa[:nx]
+                        else:
+                            b[imx, :] -= fa[:ny]
+                if mx:
+                    b[imx, :] = 0.0
+                if my:
+                    b[:, jmy] = 0.0
+                vx, vy = (0 if ox_hi else 1) + (2 if mx else 0), (0 if oy_hi else 1) + (2 if my else 0)
+                ax, ay, kbwt = hdy * ct, hdx * sn, kbar * wt
+                zz = fd_solve(fd, nx, ny, vx, vy, kbwt, ax, ay, b)
+                for _ in range(ncorr):
+                    v = mk * wt * zz - (wy[None, :] * ax * (Sx @ zz) + wx[:, None] * ay * (zz @ Sy.T))
+                    io, jo = (nx - 1 if ox_hi else 0), (ny - 1 if oy_hi else 0)
+                    v[io, :] += wy * abs(ax) * zz[io, :]
+                    v[:, jo] += wx * abs(ay) * zz[:, jo]
+                    res = b - v
+                    if mx:
+                        res[imx, :] = 0.0
+                    if my:
+                        res[:, jmy] = 0.0
+                    zz = zz + fd_solve(fd, nx, ny, vx, vy, kbwt, ax, ay, res)
+                z[soff + np.arange(nn) * ntp + th] = zz.reshape(-1)
+    return z

@@ -164,7 +164,7 @@ def test_projection_vector_round_trip_and_file(tmp_path):
     assert vec.size == m.get_ndof()
     assert Projection(m).from_vector(vec) == proj
     m.to_file(str(tmp_path / "mesh.json"))
-    proj.to_file(str(tmp_path / "proj.npy"))
+    proj.to_file(str(tmp_path / "proj.npy"), mesh_file_path=str(tmp_path / "mesh.json"))
     assert from_file(str(tmp_path / "mesh.json"), str(tmp_path / "proj.npy")) == proj
     # raw float64 dump, byte-compatible with the reference's np.fromfile reader
     assert np.array_equal(np.fromfile(str(tmp_path / "proj.npy")), vec)
