@@ -194,17 +194,28 @@ class Problem:
             nx, ny = col.ndofs
             xb, _, yb, _, _, _ = quad_xyth(nnodes_x=nx, nnodes_y=ny)
             X, Y = push_forward(x0, x1, xb), push_forward(y0, y1, yb)
-            for _, cell in sorted(col.cells.items()):
+            cells = sorted(col.cells.items())
+            if not any(dirac):
+                for _, cell in cells:
+                    assert cell.is_lf
+                    th0, th1 = cell.pos
+                    _, _, _, _, thb, _ = quad_xyth(nnodes_th=cell.ndofs[0])
+                    parts.append(_eval_nodal(bcs, X, Y, push_forward(th0, th1, thb)).reshape(-1))
+                continue
+            # Dirac source (boundary_conditions_vector.py:142-196): sample at the source location,
+            # weight by the (clipped) cardinal functions there.  The reference writes the cells
+            # of a column through ONE running index that it only advances for cells where
+            # ``any(in_cell)`` holds (:163-196) -- a cell that lies outside the source in all
+            # three coordinates leaves it where it is, so the values of the cells after it land
+            # earlier in the column block and its tail stays zero.  Reproduced as is.
+            col_vec = np.zeros(sum(nx * ny * cell.ndofs[0] for _, cell in cells))
+            idx = 0
+            for _, cell in cells:
                 assert cell.is_lf
                 th0, th1 = cell.pos
                 nth = cell.ndofs[0]
                 _, _, _, _, thb, _ = quad_xyth(nnodes_th=nth)
                 Th = push_forward(th0, th1, thb)
-                if not any(dirac):
-                    parts.append(_eval_nodal(bcs, X, Y, Th).reshape(-1))
-                    continue
-                # Dirac source: sample at the source location, weight by the
-                # (clipped) cardinal functions there.
                 lo, hi, nodes = (x0, y0, th0), (x1, y1, th1), (xb, yb, thb)
                 inside, ref = [True] * 3, [None] * 3
                 for d in range(3):
@@ -213,23 +224,26 @@ class Problem:
                             inside[d] = False
                         else:
                             ref[d] = pull_back(lo[d], hi[d], dirac[d])
+                if not any(inside):
+                    continue
+                grids = (X, Y, Th)
+
+                def factor(d, k):
+                    if dirac[d] is not None and inside[d]:
+                        return max(0.0, lag_eval(nodes[d], k, ref[d])), dirac[d]
+                    return 1., grids[d][k]
+
                 vals = np.zeros((nx, ny, nth))
-                if any(inside):
-                    grids = (X, Y, Th)
-
-                    def factor(d, k):
-                        if dirac[d] is not None and inside[d]:
-                            return max(0.0, lag_eval(nodes[d], k, ref[d])), dirac[d]
-                        return 1., grids[d][k]
-
-                    for i in range(nx):
-                        pi, xi = factor(0, i)
-                        for j in range(ny):
-                            pj, yj = factor(1, j)
-                            for a in range(nth):
-                                pa, ta = factor(2, a)
-                                vals[i, j, a] = bcs(xi, yj, ta) * pi * pj * pa
-                parts.append(vals.reshape(-1))
+                for i in range(nx):
+                    pi, xi = factor(0, i)
+                    for j in range(ny):
+                        pj, yj = factor(1, j)
+                        for a in range(nth):
+                            pa, ta = factor(2, a)
+                            vals[i, j, a] = bcs(xi, yj, ta) * pi * pj * pa
+                col_vec[idx:idx + vals.size] = vals.reshape(-1)
+                idx += vals.size
+            parts.append(col_vec)
         return np.concatenate(parts)
 
     # ---- solve ------------------------------------------------------------ #
@@ -320,7 +334,8 @@ class Problem:
                        "layout": op.flat.stats(), "true_residual_norm": info["true_res_norm"],
                        "operator_applies": info["n_apply"],
                        "ksp_type": opts["ksp_type"], "pc_type_requested": pc_type,
-                       "pc_type_used": pc_kind, "ranks": nranks,
+                       "pc_type_used": {"node": "node_bjacobi", "element": "element_bjacobi"}.get(pc_kind, pc_kind),
+                       "ranks": nranks,
                        "time_tables_s": t_tables, "time_rhs_s": t_rhs, "time_solve_s": t_solve}
         if opts["verbose"]:
             cond = info["sigma_max"] / info["sigma_min"] if info["sigma_min"] else consts.INF

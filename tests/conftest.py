@@ -46,3 +46,13 @@ def rel_err(a, b):
 @pytest.fixture(scope="session")
 def have_reference():
     return os.path.isdir("/root/reference/src")
+
+
+def mesh_digest(mesh) -> str:
+    """sha256 of the leaves of a mesh (column keys, orders, cell keys, orders): equal for the
+    reference's Mesh and rt_b200.dg.mesh.Mesh when they describe the same hp mesh."""
+    import hashlib
+    desc = [(int(ck), tuple(int(n) for n in col.ndofs),
+             tuple((int(k), int(c.ndofs[0])) for k, c in sorted(col.cells.items())))
+            for ck, col in sorted(mesh.cols.items())]
+    return hashlib.sha256(repr(desc).encode()).hexdigest()

@@ -407,3 +407,46 @@ def sweep_pc(flat, coef, fd, r, couple=True, ncorr=0):
                     zz = zz + fd_solve(fd, nx, ny, vx, vy, kbwt, ax, ay, res)
                 z[soff + np.arange(nn) * ntp + th] = zz.reshape(-1)
     return z
+
+
+# --------------------------------------------------------------------------- #
+# boundary convection on a UNIFORM mesh as a shifted gather (plain PyTorch)
+# --------------------------------------------------------------------------- #
+def bc_uniform_torch(flat, x):
+    """+BC x on a uniformly refined mesh (every face conforming, one angular signature), x a
+    slab-order torch vector: outflow faces weigh the column's own trace, inflow faces the
+    facing trace of the upwind neighbour column (nothing on the domain boundary), each times
+    (d/2) w_q wt cos(theta - F pi/2) (boundary_convection_matrix.py:284-430 with E = diag(w),
+    E_theta = diag(wF)).  Pure slicing on the [ix, iy, i, j, theta] view: independent of the
+    kernels; pinned against the oracle's assembled BC in tests/test_layout_cpu.py."""
+    import torch
+    N, NT, ncol = int(flat.col_nx[0]), int(flat.sig_nt[0]), flat.n_col
+    m = int(round(ncol ** 0.5))
+    assert m * m == ncol and flat.n_sig == 1 and flat.sig_ntp[0] == NT
+    assert np.all(flat.col_dx == flat.col_dx[0]) and np.all(flat.col_dy == flat.col_dy[0])
+    dev = x.device
+    x5 = x.view(m, m, N, N, NT)                      # sorted keys: x index slowest, then y
+    w = torch.from_numpy(flat.lgl_w[N, :N].copy()).to(dev)
+    wF = torch.from_numpy(flat.th_wF[:, :NT].copy()).to(dev)
+    bits = torch.from_numpy(flat.th_bits[:NT].astype(np.int64)).to(dev)
+    out = [((bits >> F) & 1).to(torch.float64) for F in range(4)]
+    hdx, hdy = 0.5 * float(flat.col_dx[0]), 0.5 * float(flat.col_dy[0])
+    ref = torch.zeros_like(x5)
+    wq = w[None, None, :, None]
+    # face 0 (+x): own row i = N-1; neighbour (ix + 1) row i = 0
+    own = x5[:, :, N - 1]
+    nb = torch.zeros_like(own); nb[:-1] = x5[1:, :, 0]
+    ref[:, :, N - 1] += hdy * wq * wF[0] * (out[0] * own + (1 - out[0]) * nb)
+    # face 2 (-x): own row i = 0; neighbour (ix - 1) row i = N-1
+    own = x5[:, :, 0]
+    nb = torch.zeros_like(own); nb[1:] = x5[:-1, :, N - 1]
+    ref[:, :, 0] += hdy * wq * wF[2] * (out[2] * own + (1 - out[2]) * nb)
+    # face 1 (+y): own column j = N-1; neighbour (iy + 1) column j = 0
+    own = x5[:, :, :, N - 1]
+    nb = torch.zeros_like(own); nb[:, :-1] = x5[:, 1:, :, 0]
+    ref[:, :, :, N - 1] += hdx * wq * wF[1] * (out[1] * own + (1 - out[1]) * nb)
+    # face 3 (-y): own column j = 0; neighbour (iy - 1) column j = N-1
+    own = x5[:, :, :, 0]
+    nb = torch.zeros_like(own); nb[:, 1:] = x5[:, :-1, :, N - 1]
+    ref[:, :, :, 0] += hdx * wq * wF[3] * (out[3] * own + (1 - out[3]) * nb)
+    return ref

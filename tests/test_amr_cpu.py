@@ -16,6 +16,7 @@ from rt_b200.dg.flatmesh import FlatMesh, MeshArrays
 from rt_b200.dg.mesh import from_file as mesh_from_file
 from rt_b200.dg.projection import Projection, intg_th
 from oracle import amr_oracle as AO
+from oracle import rt_oracle as O
 
 FORM = {0: "", 1: "h", 2: "p"}
 
@@ -439,3 +440,50 @@ def test_jump_indicators_on_random_hp_meshes_equal_live_reference(seed, have_ref
                          [e_ref.cols[ck].cells[kk].error for ck, kk in order], tol)
             assert [e_mine.cols[ck].cells[kk].do_ref for ck, kk in order] == \
                 [e_ref.cols[ck].cells[kk].do_ref for ck, kk in order]
+
+
+# --------------------------------------------------------------------------- #
+# the experiment AMR loops (rt_b200.experiments.run_amr) with the device replaced by the oracle
+# and the numpy emulations: host glue + steering + refinement against the golden sequences the
+# reference's own classes produced (tests/golden/make_golden_cycles.py)
+# --------------------------------------------------------------------------- #
+class _OracleProblem:
+    """Problem stand-in whose solve() is the oracle's sparse LU (no GPU)."""
+
+    def __init__(self, prob):
+        self.p = prob
+
+    def solve(self, mesh, **kw):
+        ref = O.assemble(mesh, self.p.kappa, self.p.sigma, self.p.Phi)
+        u, _ = O.solve(ref["A"], ref["mask"], O.forcing_vector(mesh, self.p.f),
+                       O.bcs_vector(mesh, self.p.bcs_dirac[0]), direct=True)
+        conv = {"converged_reason": 2, "res_best": 0.0, "iteration_number": 0}
+        return [Projection(mesh).from_vector(u), conv, {}]
+
+
+@pytest.mark.parametrize("name,ncycles", [("one-weak-scatterer", 4), ("two-strong-scatterers", 7)])
+def test_experiment_loops_reproduce_reference_mesh_sequence(name, ncycles, emulated_device):
+    import json
+    from conftest import mesh_digest
+    from rt_b200 import configs
+    from rt_b200.experiments import STRATEGIES, run_amr
+    with open(os.path.join(GOLDEN, "cycles_%s.json" % name)) as fh:
+        gold = json.load(fh)
+    prm = gold["mesh_params"]
+    prob = {"one-weak-scatterer": configs.one_weak_scatterer,
+            "two-strong-scatterers": configs.two_strong_scatterers}[name](prm["Ls"])
+    trials = gold["trials"]
+
+    def on_trial(trial, l_mesh, uh, conv, minfo, ind):
+        want = trials[trial]
+        assert (l_mesh.get_ndof(), mesh_digest(l_mesh)) == (want["ndof"], want["digest"])
+        assert abs(ind["ang"].error - want["err_ang_jmp"]) <= 1e-9 * want["err_ang_jmp"]
+        if "spt" in ind:
+            assert abs(ind["spt"].error - want["err_spt_jmp"]) <= 1e-9 * want["err_spt_jmp"]
+
+    final, log = run_amr(_OracleProblem(prob), configs.build_mesh(**prm),
+                         STRATEGIES[name][gold["strategy"]],
+                         stopping={"max_ntrial": ncycles - 1}, hr_err_params=None,
+                         seed=None if gold["seed"] is None else gold["seed"] + 1, on_trial=on_trial)
+    assert [log[t]["ref_kind"] for t in range(ncycles)] == [t["ref_kind"] for t in trials[:ncycles]]
+    assert mesh_digest(final) == trials[ncycles]["digest"]

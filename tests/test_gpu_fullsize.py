@@ -4,9 +4,11 @@ cells, p = 4: 2.62e8 DoF), where the oracle cannot assemble a matrix:
 * the three column-local terms against a plain PyTorch FP64 reference built from the same
   host tables (mass: elementwise; scattering: the dense product x G^T per spatial node with
   cuBLAS; volume convection: two einsum contractions with the stiffness table);
+* the face terms (boundary convection) against a PyTorch restatement as a shifted gather over
+  the [ix, iy, i, j, theta] view of the vector;
 * size-independent properties: linearity, term additivity, and agreement of the two
   independently written kernels (persistent k_apply_circ7 and one-block-per-column
-  k_apply_circ), which also covers the face terms.
+  k_apply_circ).
 
 Tolerance 1e-11 relative L2 (north star, single operator applies).  Set RTB200_FULLSIZE_LEVEL
 to a smaller spatial level (default 8) to run the same checks on a smaller twin."""
@@ -84,6 +86,19 @@ def test_column_local_terms_match_a_plain_torch_reference(setup):
     t2.mul_(-(hdx[:, None, None, None] * w[None, :, None, None] * st[None, None, None, :]))
     ref.add_(t2)
     del t2
+    assert _rel(y.view_as(ref), ref) <= TOL
+
+
+def test_face_terms_match_a_plain_torch_reference(setup):
+    """Boundary convection on the uniform (all-conforming) mesh is a shifted gather: outflow
+    faces weigh the column's own trace, inflow faces the facing trace of the upwind neighbour
+    column (nothing on the domain boundary), each times (d/2) w_q wt cos(theta - F pi/2)
+    (boundary_convection_matrix.py:284-430 with E = diag(w), E_theta = diag(wF)).  Written with
+    torch slicing on the [ix, iy, i, j, theta] view -- independent of both kernels."""
+    torch, flat, op, prob, x = setup
+    from emulate import bc_uniform_torch
+    ref = bc_uniform_torch(flat, x)
+    y = op.apply_slab(x, None, 8, False)
     assert _rel(y.view_as(ref), ref) <= TOL
 
 

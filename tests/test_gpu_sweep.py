@@ -109,8 +109,10 @@ def test_sweep_beats_node_block_jacobi_on_a_streaming_dominated_mesh(torch_cuda)
     u_ref, _ = O.solve(ref["A"], ref["mask"], f, g, direct=True)
     _, c_sw, m_sw, u_sw = prob.solve(mesh, pc_type="sweep", rtol=1e-11, atol=1e-300, max_it=400,
                                      return_vector=True)
-    _, c_el, _, _ = prob.solve(mesh, pc_type="element_bjacobi", rtol=1e-11, atol=1e-300, max_it=400)
-    _, c_nd, _, _ = prob.solve(mesh, pc_type="node_bjacobi", rtol=1e-11, atol=1e-300, max_it=400)
+    _, c_el, m_el = prob.solve(mesh, pc_type="element_bjacobi", rtol=1e-11, atol=1e-300, max_it=400)
+    _, c_nd, m_nd = prob.solve(mesh, pc_type="node_bjacobi", rtol=1e-11, atol=1e-300, max_it=400)
+    assert (m_sw["pc_type_used"], m_el["pc_type_used"], m_nd["pc_type_used"]) == \
+        ("sweep", "element_bjacobi", "node_bjacobi")
     assert c_sw["converged_reason"] > 0 and c_sw["iteration_number"] <= 80
     assert rel_err(u_sw, u_ref) <= 1e-8
     assert c_nd["iteration_number"] > 2 * c_sw["iteration_number"]

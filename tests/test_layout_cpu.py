@@ -344,3 +344,20 @@ def test_random_hp_meshes_through_kernel_emulation(seed):
         yr = sign * (ref[key] @ x)
         assert rel_err(y, yr) <= 1e-12, (key, rel_err(y, yr))
     assert np.array_equal(f.interior_mask_dof(), ref["mask"].astype(bool))
+
+
+def test_torch_face_term_restatement_equals_oracle_on_a_uniform_mesh():
+    """The shifted-gather restatement of +BC that tests/test_gpu_fullsize.py checks the kernels
+    against at 2.6e8 DoF, pinned here against the oracle's assembled BC at a size it can build."""
+    import torch
+    from rt_b200 import configs
+    from rt_b200.dg.flatmesh import FlatMesh, MeshArrays
+    from oracle import rt_oracle as O
+    mesh = configs.build_mesh([3., 2.], [False, False], [5, 5, 4], nref_ang=3, nref_spt=2)
+    flat = FlatMesh(MeshArrays.uniform([3., 2.], 2, 3, [5, 5, 4]))
+    xd = np.random.default_rng(0).standard_normal(flat.n_dof)
+    perm = flat.slab_index_of_dof()
+    xs = np.zeros(flat.n_slab)
+    xs[perm] = xd
+    y = E.bc_uniform_torch(flat, torch.from_numpy(xs)).reshape(-1).numpy()[perm]
+    assert rel_err(y, O.matrix_bc(mesh) @ xd) <= 1e-13
