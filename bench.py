@@ -52,9 +52,15 @@ WORKLOADS = {
     "c1": (2, 2, [4, 4, 4]),          # 4096 DoF (BASELINE configs[0] mesh)
     # seeded synthetic hp-refined meshes (small twins of BASELINE configs[4]):
     # (spatial base level, -, -); hanging nodes, degree jumps, non-uniform angular meshes
-    "c5-small": (6, None, None),      # ~3.7e6 DoF
-    "c5-512": (-7, None, None),       # level 7 base, two levels of h-refinement: 512 x 512 finest
-    "c5": (7, None, None),            # ~1.5e7 DoF
+    # BASELINE configs[4] at spec (rt_b200.hp_spec): level-7 base, 50 % -> level 8, 25 % of those
+    # -> level 9 (512 x 512 finest), nx = ny in 3..7, 8..32 angular cells of 3..7 nodes: 2.4e8 DoF
+    "c5": ("spec", 7, 4),
+    "c5-mid": ("spec", 6, 4),         # 256 x 256 finest, ~6e7 DoF
+    "c5-small": ("spec", 5, 3),       # 128 x 128 finest, ~1.5e7 DoF
+    # round-1 twins (configs.hp_synthetic: ~480-DoF columns, 8-cell angular meshes)
+    "hp-r1-small": (6, None, None),   # ~3.7e6 DoF
+    "hp-r1-512": (-7, None, None),    # level 7 base, two levels of h-refinement
+    "hp-r1": (7, None, None),         # ~1.5e7 DoF
 }
 LS = [3.0, 2.0]
 BYTES_PER_DOF = 16.0                  # read x + write y, FP64
@@ -212,6 +218,8 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     ns, na, nd = WORKLOADS[args.workload]
+    if ns == "spec":
+        ns, na, nd = 4, None, None
     ns = abs(ns)
     arm = CpuArm(cores, (min(ns, 4), na or 5, nd or [5, 5, 5]))
     for _ in range(max(args.warmup, 1)):
@@ -255,14 +263,22 @@ def run_b200(args):
     ns, na, nd = WORKLOADS[args.workload]
     prob = configs.two_strong_scatterers(LS)
     t0 = time.perf_counter()
-    if na is None:
+    t_mesh = 0.0
+    if ns == "spec":
+        from rt_b200 import hp_spec
+        arrays = hp_spec.hp_spec_arrays(LS, base_level=na, depth=2, patch_level=nd)
+        t_mesh = time.perf_counter() - t0
+        flat = FlatMesh(arrays, rank=rank, nranks=world)
+        ns, na, nd = na + 2, None, None
+    elif na is None:
         hp_mesh = configs.hp_synthetic(LS, level=abs(ns), depth=2 if ns < 0 else 1)
+        t_mesh = time.perf_counter() - t0
         ns = abs(ns)
         flat = FlatMesh(hp_mesh, rank=rank, nranks=world)
     else:
         flat = FlatMesh(MeshArrays.uniform(LS, ns, na, nd), rank=rank, nranks=world)
     op = RTOperator(flat, prob.kappa, prob.sigma, prob.Phi, device=dev)
-    t_build = time.perf_counter() - t0
+    t_build = time.perf_counter() - t0 - t_mesh      # device tables (FlatMesh + RTOperator)
     if world > 1:
         op.comm_init(rank, world)
     n_total = flat.n_dof_global

@@ -68,14 +68,10 @@ constexpr int AP_MAXCG = 8;   // columns per group
 __host__ __device__ constexpr int ap_cg(int nn, int rows = 128) { return nn >= rows ? 1 : (rows / nn > AP_MAXCG ? AP_MAXCG : rows / nn); }
 __host__ __device__ constexpr int ap_mt(int n, int rows) { return n == 0 ? 8 : ((ap_cg(n * n, rows) * n * n + 7) / 8 > 8 ? 8 : (ap_cg(n * n, rows) * n * n + 7) / 8); }
 
-struct GroupTab {
-    const int32_t* grp_first;   // [n_groups] first entry in grp_cols
-    const int32_t* grp_count;   // [n_groups]
-    const int32_t* grp_cols;    // column indices
-};
 
 #include "apply_circ.cuh"
 #include "apply_circ7.cuh"
+#include "apply_hp.h"
 
 // TH threads per block: 256, or 128 for buckets of short rows (<= 64 angles: few n-tiles
 // and few (column, angle) items, so half the warps of a 256-thread block would idle)
@@ -421,6 +417,7 @@ static int launch_one_bucket(rtb200_ctx* ctx, const Bucket& b, unsigned terms, i
 #undef X
         return rc;
     }
+    if (b.hp) return rt_hp_launch(ctx, b, terms, interior_only, x, y, st);
     switch (b.n) {
         case 2: rc = launch_bucket<2>(ctx, b, terms, interior_only, x, y, st); break;
         case 3: rc = launch_bucket<3>(ctx, b, terms, interior_only, x, y, st); break;
@@ -499,6 +496,10 @@ int rt_apply_with_halo(rtb200_ctx* ctx, unsigned terms, int interior_only, const
 
 int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
     if (!m->lgl_w || !m->lgl_s) return rt_fail(ctx, RTB200_EINVAL, "missing LGL tables");
+    {
+        int rc = rt_hp_setup(ctx, m);
+        if (rc) return rc;
+    }
     RT_CUDA(ctx, cudaMemcpyToSymbol(c_w, m->lgl_w, sizeof(double) * (RT_MAXN + 1) * RT_MAXN));
     RT_CUDA(ctx, cudaMemcpyToSymbol(c_s, m->lgl_s,
                                     sizeof(double) * (RT_MAXN + 1) * RT_MAXN * RT_MAXN));
@@ -531,6 +532,7 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
         size_t rows_max = 0;
         size_t pc_rows_nt = 0;
         int pc_nn = 0;
+        size_t hp_smem = 0;
         std::vector<int> sigs;
         void note(int nn, int nt, int sig) {
             pc_rows_nt = std::max(pc_rows_nt, (size_t)nn * nt);
@@ -567,6 +569,32 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
                 a.note(nn, m->sig_nt[k.sig], k.sig);
             }
             continue;
+        }
+        // hp kernel (apply_hp.cuh): nx == ny == 2 .. 8, every angular cell inside one quadrant;
+        // groups of up to 64 rows, shared memory <= 110 KB when possible (two blocks per SM)
+        bool hp = ctx->use_hp && hp_supported_n(k.n);
+        if (hp) {
+            const int64_t o = m->sig_th0[k.sig];
+            for (int t = 0; t < m->sig_nt[k.sig]; ++t) hp = hp && (m->th_bits[o + t] & 15) != 0;
+        }
+        if (hp) {
+            const int nt = m->sig_nt[k.sig];
+            int hcg = std::min(HP_MAXCG, HP_ROWS / nn);
+            while (hcg > 1 && 8 * hp_smem_doubles(k.n, hcg, nt) > 110 * 1024) --hcg;
+            const size_t need = 8 * hp_smem_doubles(k.n, hcg, nt);
+            if (need <= 220 * 1024) {
+                Acc& a = acc[{k.n, -2, need > 110 * 1024 ? 1 : 0}];
+                for (size_t i = 0; i < v.size(); i += hcg) {
+                    const int cnt = (int)std::min<size_t>(hcg, v.size() - i);
+                    a.first.push_back((int32_t)a.cols.size());
+                    a.count.push_back(cnt);
+                    for (int t = 0; t < cnt; ++t) a.cols.push_back(v[i + t]);
+                }
+                a.hp_smem = std::max(a.hp_smem, need);
+                a.max_ntp = std::max(a.max_ntp, m->sig_ntp[k.sig]);
+                a.note(nn, nt, k.sig);
+                continue;
+            }
         }
         Acc& a = acc[{k.n, -1, 0}];
         for (size_t i = 0; i < v.size(); i += cg) {
@@ -613,6 +641,9 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
                 const char* env = getenv("RTB200_CIRC_HERMITIAN");
                 b.circ_herm = dmax <= 1e-13 * tmax && !(env && env[0] == '0');
             }
+        } else if (std::get<1>(kv.first) == -2) {
+            b.hp = true;
+            b.smem = a.hp_smem;
         } else {
             b.ntps = ntps_for(b.max_ntp);
             b.smem = sizeof(double) * a.rows_max * (size_t)b.ntps;

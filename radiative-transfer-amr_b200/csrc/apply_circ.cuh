@@ -58,32 +58,6 @@ struct CircCfg {
     static constexpr int MINB = SMEM > 112 * 1024 ? 1 : (SMEM > 74 * 1024 ? 2 : (THREADS <= 160 ? 3 : 2));
 };
 
-// Column metadata staged in shared memory by the first 9 threads of the block.
-struct ColMeta {
-    long long slab_off;
-    long long face_base[8];
-    double hdx, hdy;
-    int bdry, c;
-    int rs[8], exy[8], acpl[8], n1[8];
-};
-
-__device__ __forceinline__ void load_col_meta(const DevMesh& m, const int c, ColMeta& cm, const int t) {
-    if (t < 8) {
-        const int fidx = c * 8 + t;
-        cm.face_base[t] = m.face_base[fidx];
-        cm.rs[t] = m.face_rstride[fidx];
-        cm.exy[t] = m.face_exy[fidx];
-        cm.acpl[t] = m.face_acpl[fidx];
-        cm.n1[t] = m.face_n1[fidx];
-    } else if (t == 8) {
-        cm.slab_off = m.col_slab_off[c];
-        cm.hdx = 0.5 * m.col_dx[c];
-        cm.hdy = 0.5 * m.col_dy[c];
-        cm.bdry = m.col_bdry[c];
-        cm.c = c;
-    }
-}
-
 // Inflow contribution of one face through the general mortar path (hanging
 // nodes, p- or angular mismatch):
 //   g[q] = (d/2) sum_j E[j][q] sum_a Eth[a][r] u'[j][theta'(a)]

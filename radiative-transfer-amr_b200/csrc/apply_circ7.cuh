@@ -99,16 +99,6 @@ struct Circ7Cfg {
     static_assert(NW_MAX * P <= 16, "a warp transforms at most 16 sequences");
 };
 
-struct ColMeta7 {
-    ColMeta cm;
-    long long coef_off;
-};
-
-__device__ __forceinline__ void load_col_meta7(const DevMesh& m, const int c, ColMeta7& cm, const int t) {
-    load_col_meta(m, c, cm.cm, t);
-    if (t == 8) cm.coef_off = m.col_coef_off[c];
-}
-
 // ---- bulk asynchronous copies (TMA, non-tensor form) completing on an mbarrier ---- //
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, const unsigned count) {
     const unsigned b = (unsigned)__cvta_generic_to_shared(bar);

@@ -30,6 +30,48 @@ __device__ __forceinline__ bool dof_masked(int i, int j, int nx, int ny, int bdr
            ((i == 0) && (bdry & 4) && (bits & 64)) || ((j == 0) && (bdry & 8) && (bits & 128));
 }
 
+struct GroupTab {
+    const int32_t* grp_first;   // [n_groups] first entry in grp_cols
+    const int32_t* grp_count;   // [n_groups]
+    const int32_t* grp_cols;    // column indices
+};
+
+// Column metadata staged in shared memory by the first 9 threads of the block.
+struct ColMeta {
+    long long slab_off;
+    long long face_base[8];
+    double hdx, hdy;
+    int bdry, c;
+    int rs[8], exy[8], acpl[8], n1[8];
+};
+
+__device__ __forceinline__ void load_col_meta(const DevMesh& m, const int c, ColMeta& cm, const int t) {
+    if (t < 8) {
+        const int fidx = c * 8 + t;
+        cm.face_base[t] = m.face_base[fidx];
+        cm.rs[t] = m.face_rstride[fidx];
+        cm.exy[t] = m.face_exy[fidx];
+        cm.acpl[t] = m.face_acpl[fidx];
+        cm.n1[t] = m.face_n1[fidx];
+    } else if (t == 8) {
+        cm.slab_off = m.col_slab_off[c];
+        cm.hdx = 0.5 * m.col_dx[c];
+        cm.hdy = 0.5 * m.col_dy[c];
+        cm.bdry = m.col_bdry[c];
+        cm.c = c;
+    }
+}
+
+struct ColMeta7 {
+    ColMeta cm;
+    long long coef_off;
+};
+
+__device__ __forceinline__ void load_col_meta7(const DevMesh& m, const int c, ColMeta7& cm, const int t) {
+    load_col_meta(m, c, cm.cm, t);
+    if (t == 8) cm.coef_off = m.col_coef_off[c];
+}
+
 // Streaming terms of column c at angular index th (< nt), for every spatial node:
 //
 //   y[n][th] = + mk[n] wt u                                   (mass_matrix.py:145,169)

@@ -186,6 +186,8 @@ extern "C" int rtb200_set_mesh(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
         if (cv && cv[0] == '6') ctx->circ_version = 6;
         const char* hs = getenv("RTB200_HP_STREAM");
         ctx->hp_node_stream = hs && strcmp(hs, "node") == 0;
+        const char* hk = getenv("RTB200_HP_KERNEL");
+        ctx->use_hp = !(hk && strcmp(hk, "old") == 0);
     }
 
     // halo plan

@@ -48,6 +48,7 @@ struct Bucket {
     int count_int = 0, count_halo = 0;
     bool circ_herm = false;             // every block of the spectrum is Hermitian (symmetric Phi)
     bool circ_conforming = false;       // no mortar face in any column of the bucket
+    bool hp = false;                    // dense columns served by k_apply_hp (apply_hp.cuh)
     const double* circ_tab_dev = nullptr;
     // eigen-table preconditioner (precond_eig.cuh): shared-memory sizing, signatures present
     size_t pc_max_rows_nt = 0;          // max over columns of nn * nt
@@ -77,6 +78,7 @@ struct rtb200_ctx {
     const double* circ_pool_dev = nullptr;
     bool use_circ = true;          // RTB200_DENSE_SCATTERING=1 in the environment disables it
     int circ_version = 7;          // RTB200_CIRC_VERSION=6 selects the one-block-per-column kernel
+    bool use_hp = true;            // RTB200_HP_KERNEL=old keeps k_apply for every dense column
     bool hp_node_stream = false;   // RTB200_HP_STREAM=node: node-parallel streaming phase of k_apply
     int64_t launches = 0;
     int sm_count = 148;
@@ -124,6 +126,10 @@ int rt_launch_apply(rtb200_ctx* ctx, unsigned terms, int interior_only, const do
 int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m);
 int rt_apply_with_halo(rtb200_ctx* ctx, unsigned terms, int interior_only, const double* x,
                        double* y, cudaStream_t st);
+// apply_hp.cu
+int rt_hp_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m);
+int rt_hp_launch(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int interior_only, const double* x,
+                 double* y, cudaStream_t st);
 // comm.cu
 int rt_allreduce_sum(rtb200_ctx* ctx, double* buf_dev, int count, cudaStream_t st);
 void rt_comm_destroy(rtb200_ctx* ctx);

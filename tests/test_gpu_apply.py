@@ -137,6 +137,32 @@ def test_seeded_hp_synthetic_mesh_matches_oracle(level):
     assert np.all(yi[~mask] == 0.0)
 
 
+@pytest.mark.parametrize("base,patch", [(1, 1), (2, 1)])
+def test_spec_hp_mesh_twin_matches_oracle(base, patch):
+    """Small twins of the spec-size hp benchmark mesh (rt_b200.hp_spec, BASELINE configs[4]:
+    three spatial levels, nx = 3..7, angular meshes of 8..32 cells with 3..7 nodes), built as
+    arrays like bench.py does; the oracle assembles the same mesh built with refinement calls."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    from oracle import rt_oracle as O
+    from rt_b200 import configs, hp_spec
+    from rt_b200.dg.flatmesh import FlatMesh
+    from rt_b200.rt import RTOperator
+    prob = configs.two_strong_scatterers()
+    st = hp_spec.hp_spec_state(base_level=base, depth=2, patch_level=patch)
+    op = RTOperator(FlatMesh(hp_spec.hp_spec_arrays(state=st)), prob.kappa, prob.sigma, prob.Phi)
+    ref = O.assemble(hp_spec.hp_spec_mesh(state=st), prob.kappa, prob.sigma, prob.Phi)
+    x = np.random.default_rng(3).standard_normal(op.n)
+    for terms, key, sign in ((3, "MS", 1.0), (4, "IC", -1.0), (8, "BC", 1.0), (15, "A", 1.0)):
+        y = op.mult(x, terms=terms)
+        assert rel_err(y, sign * (ref[key] @ x)) <= 1e-11, (terms, rel_err(y, sign * (ref[key] @ x)))
+    mask = ref["mask"].astype(bool)
+    yi = op.mult(x * mask, interior_only=True)
+    assert rel_err(yi[mask], (ref["A"] @ (x * mask))[mask]) <= 1e-11
+    assert np.all(yi[~mask] == 0.0)
+
+
 @pytest.mark.parametrize("case", ["hp_mixed", "test_mesh_script", "periodic_small", "c1_uniform"])
 def test_node_parallel_streaming_equals_column_streaming(case, monkeypatch):
     """RTB200_HP_STREAM=node (one thread per (column, node, angle) in the streaming phase of
