@@ -580,10 +580,10 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
         if (hp) {
             const int nt = m->sig_nt[k.sig];
             int hcg = std::min(HP_MAXCG, HP_ROWS / nn);
-            while (hcg > 1 && 8 * hp_smem_doubles(k.n, hcg, nt) > 110 * 1024) --hcg;
+            while (hcg > 1 && 8 * hp_smem_doubles(k.n, hcg, nt) > 110 * 1024) --hcg;   // two blocks per SM at least
             const size_t need = 8 * hp_smem_doubles(k.n, hcg, nt);
             if (need <= 220 * 1024) {
-                Acc& a = acc[{k.n, -2, need > 110 * 1024 ? 1 : 0}];
+                Acc& a = acc[{k.n, -2, need > 110 * 1024 ? 2 : (need > 73 * 1024 ? 1 : 0)}];      // 1 / 2 / 3 blocks per SM
                 for (size_t i = 0; i < v.size(); i += hcg) {
                     const int cnt = (int)std::min<size_t>(hcg, v.size() - i);
                     a.first.push_back((int32_t)a.cols.size());
@@ -644,6 +644,27 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
         } else if (std::get<1>(kv.first) == -2) {
             b.hp = true;
             b.smem = a.hp_smem;
+            std::vector<HpGroup> recs(a.first.size());
+            for (size_t gi = 0; gi < recs.size(); ++gi) {
+                HpGroup& r = recs[gi];
+                memset(&r, 0, sizeof(r));
+                r.cg_n = a.count[gi];
+                const int c0 = a.cols[a.first[gi]];
+                r.sg = m->col_sig[c0];
+                r.nt = m->sig_nt[r.sg];
+                r.ntp = m->sig_ntp[r.sg];
+                r.tp0 = m->sig_th0[r.sg];
+                r.g_off = m->sig_g_off[r.sg];
+                for (int t = 0; t < r.cg_n; ++t) {
+                    r.cols[t] = a.cols[a.first[gi] + t];
+                    r.slab_off[t] = m->col_slab_off[r.cols[t]];
+                }
+            }
+            void* d = nullptr;
+            RT_CUDA(ctx, cudaMalloc(&d, sizeof(HpGroup) * recs.size()));
+            ctx->allocs.push_back(d);
+            RT_CUDA(ctx, cudaMemcpy(d, recs.data(), sizeof(HpGroup) * recs.size(), cudaMemcpyHostToDevice));
+            b.hp_groups_dev = d;
         } else {
             b.ntps = ntps_for(b.max_ntp);
             b.smem = sizeof(double) * a.rows_max * (size_t)b.ntps;

@@ -48,7 +48,8 @@ struct Bucket {
     int count_int = 0, count_halo = 0;
     bool circ_herm = false;             // every block of the spectrum is Hermitian (symmetric Phi)
     bool circ_conforming = false;       // no mortar face in any column of the bucket
-    bool hp = false;                    // dense columns served by k_apply_hp (apply_hp.cuh)
+    bool hp = false;                    // dense columns served by k_apply_hp (apply_hp.cu)
+    const void* hp_groups_dev = nullptr; // [n_groups] HpGroup records (apply_hp.h)
     const double* circ_tab_dev = nullptr;
     // eigen-table preconditioner (precond_eig.cuh): shared-memory sizing, signatures present
     size_t pc_max_rows_nt = 0;          // max over columns of nn * nt
