@@ -64,6 +64,7 @@ WORKLOADS = {
 }
 LS = [3.0, 2.0]
 BYTES_PER_DOF = 16.0                  # read x + write y, FP64
+SOLVE_RTOL = 1e-9                     # residual reduction asked of the time-to-solve run (error vs u_true <= 1e-8)
 
 
 def measured_peaks():
@@ -75,7 +76,36 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-FP64_PEAK_TFLOPS = 37.1   # measured on this pool with scripts/micro/fp64_peak.cu (DMMA and DFMA)
+def fp64_peak():
+    """FP64 peak (TFLOP/s) measured on this pool with scripts/micro/fp64_peak.cu (DMMA and DFMA
+    give the same number: one pipe); read from the committed log of that run."""
+    p = os.path.join(ROOT, "profiles", "r01_fp64_pipe_microbench.txt")
+    try:
+        import re
+        with open(p) as fh:
+            vals = [float(m.group(1)) for m in re.finditer(r"([0-9.]+) TFLOP/s total", fh.read())]
+        if vals:
+            return max(vals), "measured (profiles/r01_fp64_pipe_microbench.txt)"
+    except Exception:
+        pass
+    return 37.1, "fallback (round-1 measurement)"
+
+
+FP64_PEAK_TFLOPS, FP64_PEAK_SOURCE = fp64_peak()
+
+
+def kernel_source_sha(names):
+    """sha256 over the sources of a kernel: ncu-derived numbers in profiles/ are stamped with it
+    and ignored when the kernel has changed since."""
+    import hashlib
+    h = hashlib.sha256()
+    for nm in names:
+        with open(os.path.join(ROOT, "radiative-transfer-amr_b200", "csrc", nm), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+CIRC7_SOURCES = ["apply_circ7.cuh", "apply_circ.cuh", "apply_common.cuh", "fft_real.cuh"]
 
 
 class ClockSampler:
@@ -257,6 +287,13 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            os.sched_setaffinity(0, set(cores[local * per:(local + 1) * per]) or set(cores))
+        except OSError:
+            pass
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -281,6 +318,7 @@ def run_b200(args):
     t_build = time.perf_counter() - t0 - t_mesh      # device tables (FlatMesh + RTOperator)
     if world > 1:
         op.comm_init(rank, world)
+    apply_paths = op.apply_paths()
     n_total = flat.n_dof_global
     n_intr_local = int(flat.interior_mask_dof().sum()) if flat.n_dof <= 5_000_000 else None
 
@@ -303,6 +341,13 @@ def run_b200(args):
 
     x = global_vector(0.1)
     y = op.empty_slab()
+    # interior DoFs (the metric's numerator): counted on the device
+    ones = op.mask_slab(op.to_slab(torch.ones(flat.n_dof, dtype=torch.float64, device=dev)), "interior")
+    n_intr = ones.sum()
+    if world > 1:
+        dist.all_reduce(n_intr)
+    n_intr = int(round(float(n_intr)))
+    del ones
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -374,18 +419,27 @@ def run_b200(args):
                         "block-circulant FFT form instead" % (2 * nt),
                 "fp64_dense_equivalent": {
                     "tflops": scat_flops / world / (ms_step * 1e-3) / 1e12,
-                    "peak_tflops": FP64_PEAK_TFLOPS,
+                    "peak_tflops": FP64_PEAK_TFLOPS, "peak_source": FP64_PEAK_SOURCE,
                     "note": "2*Ntheta flop/DoF a dense product would need per apply, over the "
                             "apply time; above the FP64 peak when the FFT path is used "
                             "(it needs ~45 FP64 instructions/DoF instead of 320 flop)"},
                 "no_scattering": {"ms_per_step": ms_ns,
                                   "achieved": BYTES_PER_DOF * (n_total / world) / (ms_ns * 1e-3) / 1e9,
                                   "frac": BYTES_PER_DOF * (n_total / world) / (ms_ns * 1e-3) / 1e9 / hbm_peak}}
+    # DRAM bytes per launch from the committed ncu --set full capture of this kernel: used only
+    # when the kernel sources are the ones the capture was taken with
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
             with open(prof) as fh:
-                roofline["traffic"] = json.load(fh).get(args.workload)
+                ent = json.load(fh).get(args.workload)
+            sha = kernel_source_sha(CIRC7_SOURCES)
+            if isinstance(ent, dict) and ent.get("kernel_source_sha") == sha:
+                roofline["traffic"] = ent["bytes"]
+                roofline["traffic_source"] = ent.get("source")
+            elif isinstance(ent, dict):
+                roofline["traffic_note"] = ("stale: profiles/traffic.json was captured with kernel sources %s, "
+                                            "this build has %s" % (ent.get("kernel_source_sha"), sha))
         except Exception:
             pass
 
@@ -397,7 +451,11 @@ def run_b200(args):
         # on two streams with their own device buffers, so the H2D copy of step i + 1
         # overlaps the D2H copy of step i (PCIe is full duplex); with several ranks the
         # library's halo buffers are shared between applies, so steps stay on one stream.
-        nslot = 2 if world == 1 else 1
+        nslot = 2
+        # (with several ranks the halo buffers and the communicator of the context serve one
+        #  apply at a time: the applies of the two slots are chained with an event, the copies
+        #  and layout conversions of one slot still overlap the other slot's)
+        last_apply = [None]
         xh = torch.empty(op.n, dtype=torch.float64).pin_memory()
         xh.normal_(generator=torch.Generator().manual_seed(7))
         slots = []
@@ -415,7 +473,12 @@ def run_b200(args):
                 sl["xd"].copy_(xh, non_blocking=True)
                 op.to_slab(sl["xd"], sl["xs"])
                 op.mask_slab(sl["xs"], "interior")
+                if world > 1 and last_apply[0] is not None:
+                    sl["st"].wait_event(last_apply[0])
                 op.apply_slab(sl["xs"], sl["ys"], 15, True)
+                if world > 1:
+                    last_apply[0] = torch.cuda.Event()
+                    last_apply[0].record(sl["st"])
                 op.from_slab(sl["ys"], sl["yd"])
                 sl["yh"].copy_(sl["yd"], non_blocking=True)
 
@@ -447,6 +510,8 @@ def run_b200(args):
         e2e = {"value": n_total / ms_e2e / 1e6, "unit": "GDoF/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(op.n * 8), "d2h_bytes_per_step": int(op.n * 8),
                "streams": nslot, "max_abs_diff_vs_resident": chk,
+               "pcie_gbs_per_rank_each_way": op.n * 8 / (ms_e2e * 1e-3) / 1e9,
+               "cpu_affinity": sorted(os.sched_getaffinity(0))[:4] + ["..."] if hasattr(os, "sched_getaffinity") else None,
                "call": "RTOperator.to_slab + mask_slab + apply_slab + from_slab on pinned host "
                        "vectors in dof order (H2D and D2H copies inside the timed region)"}
         del xh, slots
@@ -501,7 +566,7 @@ def run_b200(args):
                         barrier()
                         l0 = op.launch_count()
                         t = time.perf_counter()
-                        info = op.gmres(b, sol, restart=restart, max_it=args.solve_max_it, rtol=1e-8,
+                        info = op.gmres(b, sol, restart=restart, max_it=args.solve_max_it, rtol=SOLVE_RTOL,
                                         atol=0.0, orth=2, pc=kind, x0_nonzero=False)
                         barrier()
                         dt = time.perf_counter() - t
@@ -515,7 +580,7 @@ def run_b200(args):
                             solves[name]["sweep"] = op.pc_sweep_info()
                     except Exception as exc:
                         solves[name] = {"error": str(exc)}
-                gm["time_to_solve"] = {"rtol": 1e-8, "max_it": args.solve_max_it, "restart": restart,
+                gm["time_to_solve"] = {"rtol": SOLVE_RTOL, "max_it": args.solve_max_it, "restart": restart,
                                        "ksp": "left-preconditioned GMRES, classical Gram-Schmidt",
                                        **solves}
                 # one preconditioner application, timed alone
@@ -571,6 +636,14 @@ def run_b200(args):
                "kind": "port", "sample": r["sample"], "assemble_s": r["t_assemble_s"],
                "host_cores_available": cores}
 
+    # ---- Problem.solve end to end (single rank): host Mesh in, Projection out ------------------ #
+    e2e_solve = None
+    if rank == 0 and world == 1 and not args.no_solve and not args.no_e2e:
+        try:
+            e2e_solve = solve_record(configs, prob)
+        except Exception as exc:      # report, do not hide
+            e2e_solve = {"error": str(exc)}
+
     # ---- hp-refined workload (BASELINE configs[4]) inside the default line ----------------- #
     # so that the driver's 1 / 2 / 4 / 8-GPU sweep of the default command also carries the
     # hp strong-scaling curve (same partition rule, same timing rules)
@@ -602,14 +675,41 @@ def run_b200(args):
                            "partition": "np.array_split of sorted column keys over %d rank(s)" % world,
                            "l2": "vectors of %.2f GB per GPU exceed the 126 MB L2; no flush needed"
                                  % (op.n_slab * 8 / 1e9),
-                           "table_build_s": t_build},
+                           "table_build_s": t_build, "apply_paths": apply_paths,
+                           "value_note": "value counts all DoFs of the mesh (rows of inflow-boundary DoFs are "
+                                         "computed and zeroed); value_interior_dof counts interior rows only"},
+                "value_interior_dof": n_intr / ms_step / 1e6, "ndof_interior": n_intr,
                 "gpu_launches": int(launches), "checksum": checksum, "rel_vs_n1": rel_vs_n1,
                 "clocks": clocks, "roofline": roofline,
-                "e2e": e2e, "gmres": gm, "amr_indicators": amr, "hp": hp, "cpu_baseline": cpu}
+                "e2e": e2e, "e2e_solve": e2e_solve, "gmres": gm, "amr_indicators": amr, "hp": hp,
+                "cpu_baseline": cpu}
         print(json.dumps(line))
     op.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def solve_record(configs, prob, nref_spt: int = 5, nref_ang: int = 5, ndofs=(5, 5, 5)):
+    """``Problem.solve(mesh)`` timed end to end through the reference-facing entry point on a
+    host ``Mesh`` object (the reference's own data structure: one Python object per column and
+    cell, so the mesh is the 32 x 32-column twin of the benchmark mesh, 4.1e6 DoF): element
+    tables, right-hand sides (host callbacks), device GMRES with the transport-sweep
+    preconditioner to rtol 1e-8, merge into a ``Projection``."""
+    t0 = time.perf_counter()
+    mesh = configs.build_mesh(LS, [False, False], list(ndofs), nref_ang=nref_ang, nref_spt=nref_spt)
+    t_mesh = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    uh, conv, info = prob.solve(mesh, ksp_type="fgmres", pc_type="bjacobi", rtol=1e-8, atol=0.0, max_it=400)
+    dt = time.perf_counter() - t0
+    return {"mesh": "uniform %dx%d columns x %d cells, ndofs %s" % (2 ** nref_spt, 2 ** nref_spt, 2 ** nref_ang,
+                                                                     list(ndofs)),
+            "ndof": int(info["ndof"]), "seconds": dt, "host_mesh_build_s": t_mesh,
+            "tables_s": info["time_tables_s"], "rhs_s": info["time_rhs_s"], "solve_s": info["time_solve_s"],
+            "projection_and_merge_s": dt - info["time_tables_s"] - info["time_rhs_s"] - info["time_solve_s"],
+            "iterations": conv["iteration_number"], "converged_reason": conv["converged_reason"],
+            "pc_type_used": info["pc_type_used"], "ksp_type": info["ksp_type"],
+            "call": "Problem.solve(mesh, ksp_type='fgmres', pc_type='bjacobi') -> [Projection, convergence_info, "
+                    "matrix_info]"}
 
 
 def hp_record(args, torch, dist, dev, rank, world, prob, timed, global_vector, gnorm, hbm_peak):

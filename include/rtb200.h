@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define RTB200_ABI_VERSION 6
+#define RTB200_ABI_VERSION 7
 
 /* error codes */
 #define RTB200_OK            0
@@ -378,6 +378,13 @@ int  rtb200_err_high_resolution(rtb200_ctx* ctx_lo, const double* u_lo_slab_dev,
 
 /* ---- instrumentation -------------------------------------------------- */
 int64_t rtb200_launch_count(const rtb200_ctx* ctx);      /* kernels launched so far */
+/* Which kernel serves which columns of the mesh set with rtb200_set_mesh: one line per launch
+ * bucket, "kernel<template arguments> columns=<n> groups=<n> smem=<bytes>", newline separated,
+ * NUL terminated, truncated to buf_len.  Returns the number of buckets (< 0: error).  The
+ * reference has one code path (PETSc MatMult on the assembled AIJ matrix, src/rt/solve.py:68);
+ * here the path depends on the column class, and Problem.solve reports it in
+ * matrix_info["apply_paths"]. */
+int  rtb200_apply_path(const rtb200_ctx* ctx, char* buf, int32_t buf_len);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_NXY = 12
 MAX_NTH = 16
 
@@ -101,6 +101,7 @@ SYMBOLS = {
     "rtb200_err_spatial_jump": (C.c_int, [C.c_void_p] * 9),
     "rtb200_err_high_resolution": (C.c_int, [C.c_void_p] * 11 + [C.c_int32] + [C.c_void_p] * 3),
     "rtb200_launch_count": (C.c_int64, [C.c_void_p]),
+    "rtb200_apply_path": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
 }
 
 _lib = None

@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <map>
 #include <tuple>
@@ -69,6 +70,7 @@ __host__ __device__ constexpr int ap_cg(int nn, int rows = 128) { return nn >= r
 __host__ __device__ constexpr int ap_mt(int n, int rows) { return n == 0 ? 8 : ((ap_cg(n * n, rows) * n * n + 7) / 8 > 8 ? 8 : (ap_cg(n * n, rows) * n * n + 7) / 8); }
 
 
+constexpr int RT_HALO_RESUME_SLOTS = 4096;   // blocks of a persistent apply split around a halo exchange
 #include "apply_circ.cuh"
 #include "apply_circ7.cuh"
 #include "apply_hp.h"
@@ -357,8 +359,10 @@ static bool circ_supported(int n, int nc, int p) {
 template <int N, int NC, int P>
 static int launch_circ(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int interior_only,
                        const double* x, double* y, cudaStream_t st,
-                       const int32_t* cols_dev = nullptr, int count = -1) {
+                       const int32_t* cols_dev = nullptr, int count = -1, int n_free = -1,
+                       unsigned halo_epoch = 0, int resume = 0) {
     if (count < 0) { cols_dev = b.cols_dev; count = b.count; }
+    if (n_free < 0) n_free = count;          // no column waits for a halo exchange
     if (count == 0) return RTB200_OK;
     cudaError_t e;
     if constexpr (NC >= 8) {
@@ -376,13 +380,20 @@ static int launch_circ(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int int
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::THREADS, Cfg::SMEM);
             if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
             const int grid = std::min(count, std::max(per_sm, 1) * ctx->sm_count);
+            // resume: 1 = first launch of a split apply (blocks note where they stopped),
+            //         2 = second launch (blocks start where the first one stopped)
+            if (resume && (!ctx->halo_resume_dev || grid > RT_HALO_RESUME_SLOTS))
+                return rt_fail(ctx, RTB200_ESTATE, "no resume slots for the split persistent apply");
             if (b.circ_tab_host.size() != sizeof(CircTab7<Cfg>) / sizeof(double))
                 return rt_fail(ctx, RTB200_EINVAL, "circulant table size mismatch");
             CircTab7<Cfg> T;                      // 16 M P^2 bytes, passed in the constant bank
             memcpy(&T, b.circ_tab_host.data(), sizeof(T));
             kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(ctx->dm, cols_dev, count, b.circ_sig, terms,
                                                         interior_only, b.circ_herm ? 1 : 0, x,
-                                                        ctx->ghost_dev, y, T);
+                                                        ctx->ghost_dev, y, T, n_free, ctx->halo_flag_dev,
+                                                        halo_epoch,
+                                                        resume == 2 ? ctx->halo_resume_dev : nullptr,
+                                                        resume == 1 ? ctx->halo_resume_dev : nullptr);
             ctx->launches++;
             e = cudaGetLastError();
             if (e != cudaSuccess) return rt_cuda(ctx, e, "k_apply_circ7 launch");
@@ -407,17 +418,19 @@ static int launch_circ(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int int
 
 static int launch_one_bucket(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int interior_only,
                              const double* x, double* y, cudaStream_t st,
-                             const int32_t* cols_dev = nullptr, int count = -1) {
+                             const int32_t* cols_dev = nullptr, int count = -1, int n_free = -1,
+                             unsigned halo_epoch = 0, int resume = 0) {
     int rc = RTB200_EUNSUPPORTED;
     if (b.circ_nc > 0) {
 #define X(N_, NC_, P_)                                                                  \
     if (b.n == N_ && b.circ_nc == NC_ && b.circ_p == P_)                                \
-        rc = launch_circ<N_, NC_, P_>(ctx, b, terms, interior_only, x, y, st, cols_dev, count);
+        rc = launch_circ<N_, NC_, P_>(ctx, b, terms, interior_only, x, y, st, cols_dev, count, n_free, \
+                                      halo_epoch, resume);
         RT_CIRC_COMBOS(X)
 #undef X
         return rc;
     }
-    if (b.hp) return rt_hp_launch(ctx, b, terms, interior_only, x, y, st);
+    if (b.hp) return rt_hp_launch(ctx, b, terms, interior_only, x, y, st);   // (parts: launch_bucket_part)
     switch (b.n) {
         case 2: rc = launch_bucket<2>(ctx, b, terms, interior_only, x, y, st); break;
         case 3: rc = launch_bucket<3>(ctx, b, terms, interior_only, x, y, st); break;
@@ -431,17 +444,39 @@ static int launch_one_bucket(rtb200_ctx* ctx, const Bucket& b, unsigned terms, i
     return rc;
 }
 
+// part 0: the whole bucket; 1: what reads no ghost trace; 2: the rest (multi-GPU overlap)
+static int launch_bucket_part(rtb200_ctx* ctx, const Bucket& b, int part, unsigned terms, int interior_only,
+                              const double* x, double* y, cudaStream_t st) {
+    if (part == 0 || b.n_free < 0)
+        return part == 1 ? RTB200_OK : launch_one_bucket(ctx, b, terms, interior_only, x, y, st);
+    if (b.hp) {
+        return part == 1 ? rt_hp_launch(ctx, b, terms, interior_only, x, y, st, 0, b.n_free)
+                         : rt_hp_launch(ctx, b, terms, interior_only, x, y, st, b.n_free, b.n_groups - b.n_free);
+    }
+    if (b.circ_nc > 0) {
+        return part == 1 ? launch_one_bucket(ctx, b, terms, interior_only, x, y, st, b.cols_dev, b.n_free)
+                         : launch_one_bucket(ctx, b, terms, interior_only, x, y, st, b.cols_dev + b.n_free,
+                                             b.count - b.n_free);
+    }
+    return part == 1 ? RTB200_OK : launch_one_bucket(ctx, b, terms, interior_only, x, y, st);
+}
+
 // The buckets of an hp mesh (one per compile-time size and kernel family) read the same x
 // and write disjoint slabs of y, and most of them are too small to fill the GPU: they are
 // launched on a few side streams forked from / joined to the caller's stream, largest
 // bucket first, so that their tails overlap instead of adding up.
+// halo_ev != nullptr: the halo exchange of this apply is in flight on another stream and
+// completes with that event; every bucket launches what reads no ghost trace first.
 int rt_launch_apply(rtb200_ctx* ctx, unsigned terms, int interior_only, const double* x,
-                    double* y, cudaStream_t st) {
+                    double* y, cudaStream_t st, cudaEvent_t halo_ev) {
     const size_t nb = ctx->buckets.size();
     if (nb <= 1 || ctx->side_streams.empty()) {
-        for (const Bucket& b : ctx->buckets) {
-            int rc = launch_one_bucket(ctx, b, terms, interior_only, x, y, st);
-            if (rc) return rc;
+        for (int part = halo_ev ? 1 : 0; part <= (halo_ev ? 2 : 0); ++part) {
+            if (part == 2) RT_CUDA(ctx, cudaStreamWaitEvent(st, halo_ev, 0));
+            for (const Bucket& b : ctx->buckets) {
+                int rc = launch_bucket_part(ctx, b, part, terms, interior_only, x, y, st);
+                if (rc) return rc;
+            }
         }
         return RTB200_OK;
     }
@@ -450,12 +485,18 @@ int rt_launch_apply(rtb200_ctx* ctx, unsigned terms, int interior_only, const do
     for (size_t s = 0; s < std::min(ns, nb - 1); ++s)
         RT_CUDA(ctx, cudaStreamWaitEvent(ctx->side_streams[s], ctx->ev_fork, 0));
     int rc = RTB200_OK;
-    for (size_t i = 0; i < nb && rc == RTB200_OK; ++i) {
-        const Bucket& b = ctx->buckets[ctx->bucket_order[i]];
-        // slot 0 is the caller's stream, slots 1.. the side streams
-        const size_t slot = i % (std::min(ns, nb - 1) + 1);
-        rc = launch_one_bucket(ctx, b, terms, interior_only, x, y,
-                               slot == 0 ? st : ctx->side_streams[slot - 1]);
+    for (int part = halo_ev ? 1 : 0; part <= (halo_ev ? 2 : 0) && rc == RTB200_OK; ++part) {
+        if (part == 2) {
+            cudaStreamWaitEvent(st, halo_ev, 0);
+            for (size_t s = 0; s < std::min(ns, nb - 1); ++s) cudaStreamWaitEvent(ctx->side_streams[s], halo_ev, 0);
+        }
+        for (size_t i = 0; i < nb && rc == RTB200_OK; ++i) {
+            const Bucket& b = ctx->buckets[ctx->bucket_order[i]];
+            // slot 0 is the caller's stream, slots 1.. the side streams
+            const size_t slot = i % (std::min(ns, nb - 1) + 1);
+            rc = launch_bucket_part(ctx, b, part, terms, interior_only, x, y,
+                                    slot == 0 ? st : ctx->side_streams[slot - 1]);
+        }
     }
     for (size_t s = 0; s < std::min(ns, nb - 1); ++s) {      // always join, also after an error
         cudaEventRecord(ctx->ev_join[s], ctx->side_streams[s]);
@@ -468,6 +509,11 @@ int rt_launch_apply(rtb200_ctx* ctx, unsigned terms, int interior_only, const do
 // circulant bucket (the benchmark case) the columns that read no ghost trace are processed
 // while the exchange (k_pack + grouped ncclSend / ncclRecv) runs on the communication
 // stream; the few columns next to another rank's slab follow once the traces have landed.
+__global__ void k_set_flag(unsigned* flag, unsigned value) {
+    __threadfence();
+    atomicExch(flag, value);
+}
+
 int rt_apply_with_halo(rtb200_ctx* ctx, unsigned terms, int interior_only, const double* x,
                        double* y, cudaStream_t st) {
     if ((terms & RTB200_TERM_BCONV) && !ctx->peer_rank.empty() && (ctx->nranks <= 1 || !ctx->nccl_comm))
@@ -478,15 +524,45 @@ int rt_apply_with_halo(rtb200_ctx* ctx, unsigned terms, int interior_only, const
         return rt_launch_apply(ctx, terms, interior_only, x, y, st);
     int rc;
     if (!ctx->overlap_ready) {
-        rc = rtb200_halo_exchange(ctx, x, (void*)st);
+        if (!ctx->overlap_multi) {
+            rc = rtb200_halo_exchange(ctx, x, (void*)st);
+            if (rc) return rc;
+            return rt_launch_apply(ctx, terms, interior_only, x, y, st);
+        }
+        // several buckets (hp mesh): exchange on the communication stream, the ghost-free part
+        // of every bucket meanwhile
+        RT_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+        RT_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_fork, 0));
+        rc = rtb200_halo_exchange(ctx, x, (void*)ctx->comm_stream);
         if (rc) return rc;
-        return rt_launch_apply(ctx, terms, interior_only, x, y, st);
+        RT_CUDA(ctx, cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
+        return rt_launch_apply(ctx, terms, interior_only, x, y, st, ctx->ev_halo);
     }
     const Bucket& b = ctx->buckets[0];
     RT_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
     RT_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_fork, 0));
     rc = rtb200_halo_exchange(ctx, x, (void*)ctx->comm_stream);
     if (rc) return rc;
+    if (ctx->halo_fused && b.cols_all_dev && b.circ_conforming && b.circ_nc >= 8 && ctx->circ_version >= 7) {
+        // ONE persistent pass over all columns, those that read no ghost trace first.  The
+        // communication stream raises a flag after the exchange; a block that reaches its first
+        // ghost-reading column with the flag up carries on (the usual case: the exchange is much
+        // shorter than the interior work and the pipeline of the block stays warm), one that finds
+        // it down notes its position and exits (it never spins: a persistent grid that waits can
+        // keep the exchange's kernels off the SMs).  A second launch of the same grid, ordered
+        // after the exchange, finishes what is left: normally every block returns at once.
+        const unsigned epoch = ++ctx->halo_epoch;
+        k_set_flag<<<1, 1, 0, ctx->comm_stream>>>(ctx->halo_flag_dev, epoch);
+        ctx->launches++;
+        RT_CUDA(ctx, cudaGetLastError());
+        RT_CUDA(ctx, cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
+        const int all = b.count_int + b.count_halo;
+        rc = launch_one_bucket(ctx, b, terms, interior_only, x, y, st, b.cols_all_dev, all, b.count_int,
+                               epoch, 1);
+        cudaStreamWaitEvent(st, ctx->ev_halo, 0);      // always rejoin
+        if (rc) return rc;
+        return launch_one_bucket(ctx, b, terms, interior_only, x, y, st, b.cols_all_dev, all, all, epoch, 2);
+    }
     RT_CUDA(ctx, cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
     rc = launch_one_bucket(ctx, b, terms, interior_only, x, y, st, b.cols_int_dev, b.count_int);
     cudaStreamWaitEvent(st, ctx->ev_halo, 0);          // always rejoin
@@ -645,6 +721,7 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
             b.hp = true;
             b.smem = a.hp_smem;
             std::vector<HpGroup> recs(a.first.size());
+            std::vector<char> reads_ghost(recs.size(), 0);
             for (size_t gi = 0; gi < recs.size(); ++gi) {
                 HpGroup& r = recs[gi];
                 memset(&r, 0, sizeof(r));
@@ -658,7 +735,18 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
                 for (int t = 0; t < r.cg_n; ++t) {
                     r.cols[t] = a.cols[a.first[gi] + t];
                     r.slab_off[t] = m->col_slab_off[r.cols[t]];
+                    for (int f = 0; f < 8; ++f) reads_ghost[gi] |= m->face_base[r.cols[t] * 8 + f] <= -2;
                 }
+            }
+            if (m->n_peer > 0) {          // groups that read no ghost trace first
+                std::vector<HpGroup> ordered;
+                ordered.reserve(recs.size());
+                for (size_t gi = 0; gi < recs.size(); ++gi)
+                    if (!reads_ghost[gi]) ordered.push_back(recs[gi]);
+                b.n_free = (int)ordered.size();
+                for (size_t gi = 0; gi < recs.size(); ++gi)
+                    if (reads_ghost[gi]) ordered.push_back(recs[gi]);
+                recs.swap(ordered);
             }
             void* d = nullptr;
             RT_CUDA(ctx, cudaMalloc(&d, sizeof(HpGroup) * recs.size()));
@@ -670,6 +758,17 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
             b.smem = sizeof(double) * a.rows_max * (size_t)b.ntps;
             if (b.smem > 227 * 1024)
                 return rt_fail(ctx, RTB200_EUNSUPPORTED, "a column slab exceeds 227 KB of shared memory");
+        }
+        if (m->n_peer > 0 && b.circ_nc > 0) {
+            std::vector<int32_t> ci, ch;
+            for (int32_t c : a.cols) {
+                bool ghost = false;
+                for (int f = 0; f < 8; ++f) ghost = ghost || m->face_base[c * 8 + f] <= -2;
+                (ghost ? ch : ci).push_back(c);
+            }
+            b.n_free = (int)ci.size();
+            ci.insert(ci.end(), ch.begin(), ch.end());
+            a.cols.swap(ci);              // (one column per group: first / count stay valid)
         }
         auto up = [&](const std::vector<int32_t>& h, int32_t** d) -> int {
             RT_CUDA(ctx, cudaMalloc((void**)d, sizeof(int32_t) * h.size()));
@@ -706,6 +805,19 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
         int rc;
         if ((rc = up1(ci, &b.cols_int_dev))) return rc;
         if ((rc = up1(ch, &b.cols_halo_dev))) return rc;
+        {
+            std::vector<int32_t> all(ci);
+            all.insert(all.end(), ch.begin(), ch.end());
+            if ((rc = up1(all, &b.cols_all_dev))) return rc;
+            if (!ctx->halo_flag_dev) {
+                RT_CUDA(ctx, cudaMalloc((void**)&ctx->halo_flag_dev, sizeof(unsigned)));
+                ctx->allocs.push_back(ctx->halo_flag_dev);
+                RT_CUDA(ctx, cudaMemset(ctx->halo_flag_dev, 0, sizeof(unsigned)));
+                ctx->halo_epoch = 0;
+                RT_CUDA(ctx, cudaMalloc((void**)&ctx->halo_resume_dev, sizeof(int) * RT_HALO_RESUME_SLOTS));
+                ctx->allocs.push_back(ctx->halo_resume_dev);
+            }
+        }
         b.count_int = (int)ci.size();
         b.count_halo = (int)ch.size();
         if (!ctx->comm_stream) {
@@ -715,6 +827,18 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
         }
         const char* env = getenv("RTB200_HALO_OVERLAP");
         ctx->overlap_ready = !(env && env[0] == '0');
+        const char* fenv = getenv("RTB200_HALO_FUSED");
+        ctx->halo_fused = !(fenv && fenv[0] == '0');
+    }
+    ctx->overlap_multi = false;
+    if (m->n_peer > 0 && !ctx->overlap_ready) {
+        if (!ctx->comm_stream) {
+            RT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+            RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
+        }
+        if (!ctx->ev_fork) RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        const char* env = getenv("RTB200_HALO_OVERLAP");
+        ctx->overlap_multi = !(env && env[0] == '0');
     }
     // launch order: most columns x angles first
     ctx->bucket_order.resize(ctx->buckets.size());
@@ -734,7 +858,7 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
             RT_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             ctx->ev_join.push_back(ev);
         }
-        RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        if (!ctx->ev_fork) RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     }
     return RTB200_OK;
 }
@@ -787,6 +911,29 @@ extern "C" int rtb200_mask(rtb200_ctx* ctx, double* x_slab_dev, int keep, void* 
     ctx->launches++;
     RT_CUDA(ctx, cudaGetLastError());
     return RTB200_OK;
+}
+
+extern "C" int rtb200_apply_path(const rtb200_ctx* ctx, char* buf, int32_t buf_len) {
+    if (!ctx || !buf || buf_len <= 0) return RTB200_EINVAL;
+    if (!ctx->have_mesh) return RTB200_ESTATE;
+    std::string s;
+    char line[256];
+    for (const Bucket& b : ctx->buckets) {
+        if (b.circ_nc > 0) {
+            const bool v7 = b.circ_nc >= 8 && ctx->circ_version >= 7 && b.circ_conforming;
+            snprintf(line, sizeof(line), "%s<%d,%d,%d> columns=%d groups=%d\n",
+                     v7 ? "k_apply_circ7" : "k_apply_circ", b.n, b.circ_nc, b.circ_p, b.count, b.count);
+        } else if (b.hp) {
+            snprintf(line, sizeof(line), "k_apply_hp<%d> columns=%d groups=%d smem=%zu\n", b.n, b.count,
+                     b.n_groups, b.smem);
+        } else {
+            snprintf(line, sizeof(line), "k_apply<%d,%d> columns=%d groups=%d smem=%zu\n", b.n,
+                     b.max_ntp <= 64 ? 128 : 256, b.count, b.n_groups, b.smem);
+        }
+        s += line;
+    }
+    snprintf(buf, (size_t)buf_len, "%s", s.c_str());
+    return (int)ctx->buckets.size();
 }
 
 // node-wise block-Jacobi preconditioner (shares the transforms of k_apply_circ7)

@@ -607,7 +607,9 @@ template <int N, int NC, int P>
 __global__ void __launch_bounds__(Circ7Cfg<N, NC, P>::THREADS, Circ7Cfg<N, NC, P>::MINB)
 k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int sg, unsigned terms,
               int interior_only, int herm, const double* __restrict__ x, const double* __restrict__ ghost,
-              double* __restrict__ y, const __grid_constant__ CircTab7<Circ7Cfg<N, NC, P>> T) {
+              double* __restrict__ y, const __grid_constant__ CircTab7<Circ7Cfg<N, NC, P>> T,
+              const int n_free, const unsigned* __restrict__ halo_flag, const unsigned halo_epoch,
+              const int* __restrict__ resume_in, int* __restrict__ resume_out) {
     using Cfg = Circ7Cfg<N, NC, P>;
     constexpr int NN = Cfg::NN, NT = Cfg::NT, NTP = Cfg::NTP;
     constexpr int SU = Cfg::SU, THREADS = Cfg::THREADS;
@@ -621,8 +623,18 @@ k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int 
     __shared__ __align__(8) unsigned long long s_bar[2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int stride = gridDim.x;
-    int it = blockIdx.x;
-    if (it >= ncols) return;
+    // Multi-GPU (rt_apply_with_halo): the columns from position n_free on read ghost traces.
+    // Launch 1 runs while the exchange is in flight: a block that reaches its first such column
+    // before the exchange has published its epoch in *halo_flag does NOT wait (a persistent
+    // grid that spins can keep the exchange's own kernels off the SMs for ever): it notes
+    // where it stopped in resume_out and exits; launch 2, ordered after the exchange, starts
+    // every block at resume_in.  Blocks that find the flag raised simply carry on.
+    int it = resume_in ? resume_in[blockIdx.x] : blockIdx.x;
+    if (it >= ncols) {
+        if (resume_out && threadIdx.x == 0) resume_out[blockIdx.x] = it;
+        return;
+    }
+    __shared__ int s_go;
 
     // ---- prologue: per-angle tables, block spectrum, metadata of the first two columns -- //
     {
@@ -669,8 +681,22 @@ k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int 
     const int half = tid >= Cfg::NTW ? 1 : 0;
     const int th = tid - half * Cfg::NTW;
     int cur = 0, ms = 0;
+    bool halo_ok = false;
     unsigned phase = 0;      // bit b: parity of the next completion of buffer b
     for (; it < ncols; it += stride) {
+        if (it >= n_free && !halo_ok) {
+            if (tid == 0) {
+                unsigned seen;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(halo_flag) : "memory");
+                s_go = (int)(seen - halo_epoch) >= 0;
+            }
+            __syncthreads();
+            if (!s_go) {
+                mbar_wait(&s_bar[cur], (phase >> cur) & 1u);     // the copy of this column is in flight
+                break;
+            }
+            halo_ok = true;
+        }
         __syncthreads();     // everybody is done with the previous column (U[cur ^ 1], W are free)
         const int ms1 = ms == 2 ? 0 : ms + 1, ms2 = ms1 == 2 ? 0 : ms1 + 1;
         if (it + stride < ncols) prefetch(cur ^ 1, s_meta[ms1]);
@@ -717,4 +743,5 @@ k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int 
         cur ^= 1;
         ms = ms1;
     }
+    if (resume_out && tid == 0) resume_out[blockIdx.x] = it;
 }

@@ -470,7 +470,8 @@ k_apply_hp(DevMesh m, const HpGroup* __restrict__ groups, unsigned terms, int in
 
 template <int N>
 static int launch_hp(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int interior_only,
-                     const double* x, double* y, cudaStream_t st) {
+                     const double* x, double* y, cudaStream_t st, int group0, int n_groups) {
+    if (n_groups == 0) return RTB200_OK;
     auto kern = k_apply_hp<N>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b.smem);
     if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaFuncSetAttribute(k_apply_hp, smem)");
@@ -482,8 +483,8 @@ static int launch_hp(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int inter
         e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaFuncSetAttribute(k_apply_hp, carveout)");
     }
-    kern<<<b.n_groups, HP_THREADS, b.smem, st>>>(ctx->dm, static_cast<const HpGroup*>(b.hp_groups_dev), terms,
-                                                   interior_only, x, ctx->ghost_dev, y);
+    kern<<<n_groups, HP_THREADS, b.smem, st>>>(ctx->dm, static_cast<const HpGroup*>(b.hp_groups_dev) + group0,
+                                                 terms, interior_only, x, ctx->ghost_dev, y);
     ctx->launches++;
     e = cudaGetLastError();
     if (e != cudaSuccess) return rt_cuda(ctx, e, "k_apply_hp launch");
@@ -497,15 +498,16 @@ int rt_hp_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
 }
 
 int rt_hp_launch(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int interior_only, const double* x,
-                 double* y, cudaStream_t st) {
+                 double* y, cudaStream_t st, int group0, int n_groups) {
+    if (n_groups < 0) n_groups = b.n_groups - group0;
     switch (b.n) {
-        case 2: return launch_hp<2>(ctx, b, terms, interior_only, x, y, st);
-        case 3: return launch_hp<3>(ctx, b, terms, interior_only, x, y, st);
-        case 4: return launch_hp<4>(ctx, b, terms, interior_only, x, y, st);
-        case 5: return launch_hp<5>(ctx, b, terms, interior_only, x, y, st);
-        case 6: return launch_hp<6>(ctx, b, terms, interior_only, x, y, st);
-        case 7: return launch_hp<7>(ctx, b, terms, interior_only, x, y, st);
-        case 8: return launch_hp<8>(ctx, b, terms, interior_only, x, y, st);
+        case 2: return launch_hp<2>(ctx, b, terms, interior_only, x, y, st, group0, n_groups);
+        case 3: return launch_hp<3>(ctx, b, terms, interior_only, x, y, st, group0, n_groups);
+        case 4: return launch_hp<4>(ctx, b, terms, interior_only, x, y, st, group0, n_groups);
+        case 5: return launch_hp<5>(ctx, b, terms, interior_only, x, y, st, group0, n_groups);
+        case 6: return launch_hp<6>(ctx, b, terms, interior_only, x, y, st, group0, n_groups);
+        case 7: return launch_hp<7>(ctx, b, terms, interior_only, x, y, st, group0, n_groups);
+        case 8: return launch_hp<8>(ctx, b, terms, interior_only, x, y, st, group0, n_groups);
         default: return rt_fail(ctx, RTB200_EUNSUPPORTED, "k_apply_hp: order not compiled");
     }
 }

@@ -46,6 +46,8 @@ extern "C" int rtb200_create(int device, rtb200_ctx** out) {
 static void free_tables(rtb200_ctx* ctx) {
     for (void* p : ctx->allocs) cudaFree(p);
     ctx->allocs.clear();
+    ctx->halo_flag_dev = nullptr;      // lives in allocs
+    ctx->halo_resume_dev = nullptr;
     ctx->buckets.clear();
     ctx->coef_dev = nullptr;
     ctx->ghost_dev = nullptr;

@@ -492,7 +492,7 @@ int rt_sweep_apply(rtb200_ctx* ctx, int pc_type, const double* r, double* z, cud
     if (S->n_items == 0) return RTB200_OK;
     // defect-correction steps of the local solves: contraction factor rho per step
     int ncorr = ctx->pc_ncorr;
-    if (ncorr < 0) ncorr = S->rho_max <= 0.15 ? 0 : (S->rho_max <= 0.5 ? 1 : 2);
+    if (ncorr < 0) ncorr = S->rho_max <= 0.5 ? 0 : (S->rho_max <= 0.85 ? 1 : 2);
     const char* env = getenv("RTB200_PC_NCORR");
     if (env && env[0] >= '0' && env[0] <= '9') ncorr = env[0] - '0';
     // one launch per (level, kernel class); the element-wise block-Jacobi has no coupling, so all

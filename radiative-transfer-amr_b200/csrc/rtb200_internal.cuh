@@ -45,11 +45,15 @@ struct Bucket {
     int circ_nc = 0, circ_p = 0, circ_sig = 0;
     int32_t* cols_int_dev = nullptr;    // multi-GPU: columns that read no ghost trace ...
     int32_t* cols_halo_dev = nullptr;   // ... and those that do (rt_apply_with_halo)
+    int32_t* cols_all_dev = nullptr;    // both lists back to back (single launch with a device-side wait)
     int count_int = 0, count_halo = 0;
     bool circ_herm = false;             // every block of the spectrum is Hermitian (symmetric Phi)
     bool circ_conforming = false;       // no mortar face in any column of the bucket
     bool hp = false;                    // dense columns served by k_apply_hp (apply_hp.cu)
     const void* hp_groups_dev = nullptr; // [n_groups] HpGroup records (apply_hp.h)
+    // multi-GPU: the first n_free groups (hp) / columns (circulant) read no ghost trace and are
+    // launched while the halo exchange is in flight (-1: the bucket is not split)
+    int n_free = -1;
     const double* circ_tab_dev = nullptr;
     // eigen-table preconditioner (precond_eig.cuh): shared-memory sizing, signatures present
     size_t pc_max_rows_nt = 0;          // max over columns of nn * nt
@@ -74,6 +78,11 @@ struct rtb200_ctx {
     cudaStream_t comm_stream = nullptr;         // halo exchange overlapped with interior columns
     cudaEvent_t ev_halo = nullptr;
     bool overlap_ready = false;
+    bool overlap_multi = false;        // several buckets: ghost-free parts overlap the exchange
+    bool halo_fused = true;            // RTB200_HALO_FUSED=0: two launches (interior, then ghost-reading columns)
+    unsigned* halo_flag_dev = nullptr; // raised to the apply's epoch by the communication stream
+    unsigned halo_epoch = 0;
+    int* halo_resume_dev = nullptr;    // per block: first column the first launch of a split apply left undone
     double* coef_dev = nullptr;
     int64_t n_coef = 0;
     const double* circ_pool_dev = nullptr;
@@ -123,14 +132,14 @@ int rt_cuda(rtb200_ctx* ctx, cudaError_t e, const char* what);
 
 // apply.cu
 int rt_launch_apply(rtb200_ctx* ctx, unsigned terms, int interior_only, const double* x,
-                    double* y, cudaStream_t st);
+                    double* y, cudaStream_t st, cudaEvent_t halo_ev = nullptr);
 int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m);
 int rt_apply_with_halo(rtb200_ctx* ctx, unsigned terms, int interior_only, const double* x,
                        double* y, cudaStream_t st);
 // apply_hp.cu
 int rt_hp_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m);
 int rt_hp_launch(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int interior_only, const double* x,
-                 double* y, cudaStream_t st);
+                 double* y, cudaStream_t st, int group0 = 0, int n_groups = -1);
 // comm.cu
 int rt_allreduce_sum(rtb200_ctx* ctx, double* buf_dev, int count, cudaStream_t st);
 void rt_comm_destroy(rtb200_ctx* ctx);

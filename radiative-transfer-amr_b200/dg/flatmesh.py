@@ -350,12 +350,14 @@ class FlatMesh:
         self.face_nbr = -np.ones(nc * 8, np.int32)
         exy_pool, exy_ids = [], {}
 
+        exy_at = {}
+
         def exy_pool_view(off, n1_, n0_):
-            flat_ = np.concatenate(exy_pool)
-            return flat_[off:off + n1_ * n0_].reshape(n1_, n0_)
+            return exy_at[int(off)].reshape(n1_, n0_)
 
         eth_pool, eth_ids = [], {}
         acpl_pool, acpl_ids = [], {}
+        eth_at, acpl_tab = {}, {}          # offset -> block (no pool concatenation while building)
         n_exy = n_eth = n_acpl = 0
 
         # ghost traces: (owner, global col, side) -> offset in this rank's ghost buffer
@@ -410,7 +412,9 @@ class FlatMesh:
 
                 # spatial mortar ids (same cache key as get_Ex.py:40-44)
                 ekey = np.stack([n0, n1, dlv, rel], axis=1)
-                uk, first, inv = np.unique(ekey, axis=0, return_index=True, return_inverse=True)
+                packed = ((n0.astype(np.int64) * 64 + n1) * 64 + (dlv.astype(np.int64) + 32)) * 4 + rel
+                _, first, inv = np.unique(packed, return_index=True, return_inverse=True)
+                uk = ekey[first]
                 inv = inv.reshape(-1)
                 offs = np.zeros(len(uk), np.int32)
                 for u, (kk, ft) in enumerate(zip(uk, first)):
@@ -421,6 +425,7 @@ class FlatMesh:
                                            (pos[a, ax], pos[a, ax + 2]),
                                            (pos[b, ax], pos[b, ax + 2]))
                         exy_ids[kt] = n_exy
+                        exy_at[n_exy] = np.ascontiguousarray(E).reshape(-1)
                         exy_pool.append(np.ascontiguousarray(E).reshape(-1))
                         n_exy += E.size
                     offs[u] = exy_ids[kt]
@@ -439,7 +444,9 @@ class FlatMesh:
 
                 # angular coupling tables per (sig0, sig1, F)
                 akey = np.stack([A.sig[g0], A.sig[g1]], axis=1)
-                uk, inv = np.unique(akey, axis=0, return_inverse=True)
+                packed = akey[:, 0].astype(np.int64) * (len(A.sigs) + 1) + akey[:, 1]
+                _, first, inv = np.unique(packed, return_index=True, return_inverse=True)
+                uk = akey[first]
                 inv = inv.reshape(-1)
                 offs = np.zeros(len(uk), np.int32)
                 for u, kk in enumerate(uk):
@@ -461,10 +468,12 @@ class FlatMesh:
                                         (s0.th0[c0], s0.th1[c0]), (s1.th0[c1], s1.th1[c1]), F)
                                     Eth = Eth * ((s0.th1[c0] - s0.th0[c0]) / 2.0)
                                     eth_ids[bk] = n_eth
+                                    eth_at[n_eth] = np.ascontiguousarray(Eth)
                                     eth_pool.append(np.ascontiguousarray(Eth).reshape(-1))
                                     n_eth += Eth.size
                                 tab[c0, k] = (eth_ids[bk], int(s1.thoff[c1]), int(s1.nth[c1]))
                         acpl_ids[kt] = n_acpl
+                        acpl_tab[n_acpl] = tab
                         acpl_pool.append(tab.reshape(-1))
                         n_acpl += tab.size
                     offs[u] = acpl_ids[kt]
@@ -474,8 +483,8 @@ class FlatMesh:
                 if conforming_fast_path:
                     for u, kk in enumerate(uk):
                         if int(kk[0]) == int(kk[1]) and self._acpl_is_diagonal(
-                                A.sigs[int(kk[0])], int(kk[0]), F, acpl_pool, eth_pool,
-                                acpl_ids[(int(kk[0]), int(kk[1]), F)], eth_ids):
+                                A.sigs[int(kk[0])], int(kk[0]), F,
+                                acpl_tab[acpl_ids[(int(kk[0]), int(kk[1]), F)]], eth_at):
                             aoff = np.where(inv == u, -1, aoff)
                 self.face_acpl[fidx] = aoff
 
@@ -490,24 +499,22 @@ class FlatMesh:
         self._build_halo_plan()
 
     # ------------------------------------------------------------------ #
-    def _acpl_is_diagonal(self, sig, si, F, acpl_pool, eth_pool, tab_off, eth_ids) -> bool:
+    def _acpl_is_diagonal(self, sig, si, F, tab, eth_at) -> bool:
         """True when the (sig, sig, F) angular coupling is the pointwise upwind
         weight: every inflow cell couples to the same cell only and its scaled
         E_theta block equals diag(wF) to 1e-14."""
-        pool = np.concatenate(acpl_pool)
-        eth = np.concatenate(eth_pool)
         o = int(self.sig_th0[si])
         for c0 in range(len(sig.keys)):
-            ent = pool[tab_off + c0 * 6: tab_off + c0 * 6 + 6]
+            ent = tab[c0].reshape(-1)
             q = int(sig.quadrant[c0])
             if q >= 0 and F in _OUTFLOW[q]:
                 continue
             nth = int(sig.nth[c0])
             if ent[5] != 0 or ent[2] != nth or ent[1] != int(sig.thoff[c0]):
                 return False
-            blk = eth[ent[0]: ent[0] + nth * nth].reshape(nth, nth)
+            blk = eth_at[int(ent[0])]
             wF = self.th_wF[F, o + int(sig.thoff[c0]): o + int(sig.thoff[c0]) + nth]
-            if np.max(np.abs(blk - np.diag(wF))) > 1e-14:
+            if blk.shape != (nth, nth) or np.max(np.abs(blk - np.diag(wF))) > 1e-14:
                 return False
         return True
 

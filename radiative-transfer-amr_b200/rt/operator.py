@@ -173,7 +173,8 @@ class RTOperator:
         self.sig_g_off, self.g_pool = build_g_pool(flat, Phi)
         self.coef = sample_coefficients(flat, kappa, sigma)
         self.circ = build_circ_pool(flat, self.sig_g_off, self.g_pool)
-        self.pc_eig = build_pc_eig_pool(flat, self.sig_g_off, self.g_pool, self.circ)
+        self.pc_eig = None           # eigen tables of the node-wise block-Jacobi: built on first use
+        self._pc_kind = L.PC_NODE    # what pc_apply computes (the library's default)
         self._keep = []
         self.ctx = C.c_void_p()
         L.check(self.lib, None, self.lib.rtb200_create(self.device.index or 0, C.byref(self.ctx)),
@@ -225,11 +226,6 @@ class RTOperator:
         put("circ_pool", self.circ[3] if self.circ[3].size else np.zeros(2), np.float64, C.c_double)
         self._call("rtb200_set_mesh", self.lib.rtb200_set_mesh(self.ctx, C.byref(m)))
         keep.clear()
-        off, pool = self.pc_eig
-        if pool.size:
-            self._call("rtb200_pc_set_eig", self.lib.rtb200_pc_set_eig(
-                self.ctx, _as_c(off, C.c_int64), C.c_int32(off.size), _as_c(pool, C.c_double),
-                C.c_int64(pool.size)))
         # 1-D fast-diagonalisation tables of the transport-sweep preconditioner
         fd_off, fd_pool = T.fd_tables(L.MAX_NXY)
         self._call("rtb200_pc_set_fd", self.lib.rtb200_pc_set_fd(
@@ -238,6 +234,17 @@ class RTOperator:
 
     def _call(self, what, rc):
         L.check(self.lib, self.ctx, rc, what)
+
+    def _ensure_pc_eig(self):
+        """Upload the per-signature eigen tables the node-wise block-Jacobi needs on columns
+        without a uniform angular mesh (one ``eigh`` per signature: not paid unless used)."""
+        if self.pc_eig is None:
+            self.pc_eig = build_pc_eig_pool(self.flat, self.sig_g_off, self.g_pool, self.circ)
+            off, pool = self.pc_eig
+            if pool.size:
+                self._call("rtb200_pc_set_eig", self.lib.rtb200_pc_set_eig(
+                    self.ctx, _as_c(off, C.c_int64), C.c_int32(off.size), _as_c(pool, C.c_double),
+                    C.c_int64(pool.size)))
 
     def close(self):
         if getattr(self, "ctx", None) is not None and self.ctx.value:
@@ -326,6 +333,9 @@ class RTOperator:
         """What ``pc_apply`` computes: 'node' (node-wise (M - S)^-1), 'sweep' (transport sweep,
         (M + BC - IC)^-1 with the column mid-range extinction + ``n_corr`` local defect
         corrections, -1 = chosen from the data) or 'element' (its block-diagonal part)."""
+        self._pc_kind = int(PC_KINDS.get(kind, kind))
+        if self._pc_kind == L.PC_NODE:
+            self._ensure_pc_eig()
         self._call("rtb200_pc_set_type", self.lib.rtb200_pc_set_type(
             self.ctx, int(PC_KINDS.get(kind, kind)), int(n_corr)))
 
@@ -342,6 +352,8 @@ class RTOperator:
         ``preconditioner_matrix``: block-circulant FFT on uniform angular meshes,
         per-signature eigen tables otherwise)."""
         z_slab = self.empty_slab() if z_slab is None else z_slab
+        if self._pc_kind == L.PC_NODE:
+            self._ensure_pc_eig()
         self._call("rtb200_pc_apply", self.lib.rtb200_pc_apply(
             self.ctx, C.c_void_p(r_slab.data_ptr()), C.c_void_p(z_slab.data_ptr()), self._stream()))
         return z_slab
@@ -352,6 +364,14 @@ class RTOperator:
 
     def launch_count(self) -> int:
         return int(self.lib.rtb200_launch_count(self.ctx))
+
+    def apply_paths(self) -> list:
+        """One entry per launch bucket: which kernel serves how many columns of this mesh."""
+        buf = C.create_string_buffer(16384)
+        n = self.lib.rtb200_apply_path(self.ctx, buf, C.c_int32(len(buf)))
+        if n < 0:
+            raise L.RTB200Error("rtb200_apply_path failed (%d)" % n)
+        return [ln for ln in buf.value.decode().split("\n") if ln]
 
     def apply_kernel_name(self) -> str:
         """Name of the kernel that carries (most of) an apply on this mesh: the
@@ -373,6 +393,8 @@ class RTOperator:
         left-preconditioned default.  Returns the info dict (PETSc-style reason code,
         history, ...)."""
         pc = int(PC_KINDS.get(pc, pc))
+        if pc == L.PC_NODE:
+            self._ensure_pc_eig()
         side = 1 if (flexible and pc) else 0
         torch = _torch()
         if divtol is None:

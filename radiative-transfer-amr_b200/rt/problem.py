@@ -331,7 +331,8 @@ class Problem:
                             "rtol": rtol, "atol": atol, "divtol": divtol, "max_it": max_it}
         matrix_info = {"extreme_singular_values": [info["sigma_max"], info["sigma_min"]],
                        "ndof": op.n, "ndof_interior": int(op.flat.interior_mask_dof().sum()),
-                       "layout": op.flat.stats(), "true_residual_norm": info["true_res_norm"],
+                       "layout": op.flat.stats(), "apply_paths": op.apply_paths(),
+                       "true_residual_norm": info["true_res_norm"],
                        "operator_applies": info["n_apply"],
                        "ksp_type": opts["ksp_type"], "pc_type_requested": pc_type,
                        "pc_type_used": {"node": "node_bjacobi", "element": "element_bjacobi"}.get(pc_kind, pc_kind),
