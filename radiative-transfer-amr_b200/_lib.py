@@ -18,6 +18,10 @@ PC_NONE, PC_NODE, PC_SWEEP, PC_ELEMENT = 0, 1, 2, 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "librtb200.so")
+# kernel-tuning builds (`make lab`: one circulant instantiation, compiles in a minute) are
+# loaded only on request; the product and the tests always use librtb200.so
+if os.environ.get("RTB200_LAB_LIB") == "1":
+    LIB_PATH = os.path.join(_HERE, "csrc", "librtb200_lab.so")
 
 _i32p = C.POINTER(C.c_int32)
 _i64p = C.POINTER(C.c_int64)

@@ -347,7 +347,11 @@ static int launch_bucket(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int i
 // ((5, 8, 3) manufactured-solution, (3, 8, 4) one-weak / two-strong, input.json
 // mesh_params) and small cases for the parity tests.  Other uniform angular
 // meshes run the dense kernel.
+#ifdef RTB200_LAB      // make LAB=1: only what the c4 benchmark launches (fast kernel-tuning builds, never shipped)
+#define RT_CIRC_COMBOS(X) X(5, 32, 5)
+#else
 #define RT_CIRC_COMBOS(X) X(5, 32, 5) X(5, 8, 3) X(3, 8, 4) X(4, 16, 4) X(3, 8, 3) X(4, 4, 4)
+#endif
 
 static bool circ_supported(int n, int nc, int p) {
 #define X(N_, NC_, P_) if (n == N_ && nc == NC_ && p == P_) return true;
@@ -393,7 +397,8 @@ static int launch_circ(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int int
                                                         ctx->ghost_dev, y, T, n_free, ctx->halo_flag_dev,
                                                         halo_epoch,
                                                         resume == 2 ? ctx->halo_resume_dev : nullptr,
-                                                        resume == 1 ? ctx->halo_resume_dev : nullptr);
+                                                        resume == 1 ? ctx->halo_resume_dev : nullptr,
+                                                        ctx->circ_eo | (ctx->circ_inner << 1));
             ctx->launches++;
             e = cudaGetLastError();
             if (e != cudaSuccess) return rt_cuda(ctx, e, "k_apply_circ7 launch");
@@ -432,6 +437,7 @@ static int launch_one_bucket(rtb200_ctx* ctx, const Bucket& b, unsigned terms, i
     }
     if (b.hp) return rt_hp_launch(ctx, b, terms, interior_only, x, y, st);   // (parts: launch_bucket_part)
     switch (b.n) {
+#ifndef RTB200_LAB
         case 2: rc = launch_bucket<2>(ctx, b, terms, interior_only, x, y, st); break;
         case 3: rc = launch_bucket<3>(ctx, b, terms, interior_only, x, y, st); break;
         case 4: rc = launch_bucket<4>(ctx, b, terms, interior_only, x, y, st); break;
@@ -439,6 +445,7 @@ static int launch_one_bucket(rtb200_ctx* ctx, const Bucket& b, unsigned terms, i
         case 6: rc = launch_bucket<6>(ctx, b, terms, interior_only, x, y, st); break;
         case 7: rc = launch_bucket<7>(ctx, b, terms, interior_only, x, y, st); break;
         case 8: rc = launch_bucket<8>(ctx, b, terms, interior_only, x, y, st); break;
+#endif
         default: rc = launch_bucket<0>(ctx, b, terms, interior_only, x, y, st); break;
     }
     return rc;

@@ -218,7 +218,7 @@ __device__ __forceinline__ void split_inverse(const double2 (&ia)[NC / 8], const
 // FULL: all four terms (the solver's call); the term tests are compiled out.
 // Order: neighbour-trace loads are issued first and consumed last (L2 latency hidden
 // behind the two derivative passes over shared memory).
-template <int N, int HALF, bool FULL, typename Cfg>
+template <int N, int HALF, bool FULL, typename Cfg, bool INNER = false>
 __device__ __noinline__ void stream7(
     const ColMeta& cm, const double* __restrict__ coef_s, const double* __restrict__ tab,
     const int th, const double* __restrict__ us, const double* __restrict__ ws, const unsigned terms,
@@ -235,7 +235,7 @@ __device__ __noinline__ void stream7(
 
     const int bits = reinterpret_cast<const int*>(tab + 3 * NT)[th];
     const int Fx = (bits & 1) ? 2 : 0, Fy = (bits & 2) ? 3 : 1;        // the two inflow faces
-    const int bdry = cm.bdry;
+    const int bdry = INNER ? 0 : cm.bdry;       // INNER: column off the domain boundary (block-uniform)
 
     // inflow x-face: row N-1 when Fx == 0 (half 1), row 0 when Fx == 2 (half 0)
     constexpr int IX = HALF == 0 ? 0 : N - 1;
@@ -338,7 +338,7 @@ __device__ __noinline__ void stream7(
     }
 
     // ---- scattering combine, interior restriction (get_masks.py:80-110), store ----- //
-    const bool msk = interior_only != 0;
+    const bool msk = !INNER && interior_only != 0;
     const bool m0 = msk && (bdry & 1) && (bits & 16), m1 = msk && (bdry & 2) && (bits & 32);
     const bool m2 = msk && (bdry & 4) && (bits & 64), m3 = msk && (bdry & 8) && (bits & 128);
     double* yc = y + cm.slab_off + th;
@@ -603,14 +603,247 @@ __device__ __noinline__ void fft_i7(double* __restrict__ W, const int warp, cons
     }
 }
 
+
+// ---- scattering, E/O form (default): no cross-lane exchange at all ------------------ //
+// The two lanes of a sequence transform the even / the odd samples (length NC/2, as above)
+// and store their HALF-LENGTH spectra E, O as they are; the last radix-2 stage of the
+// forward transform and the first of the inverse move into the block-product phase, whose
+// thread (lane = node, task k warp-uniform) owns the slots k and NC/2 - k together:
+//     2 X[k]        = 2 E[k] + w^k 2 O[k],        2 X[NC/2 - k] = conj(2 E[k] - w^k 2 O[k])
+//     Y[k] = T[k] 2 X[k],   Y[NC/2 - k] = T[NC/2 - k] 2 X[NC/2 - k]
+//     A[k] = Y[k] + conj(Y[NC/2 - k])             -> even samples of the result
+//     B[k] = (Y[k] - conj(Y[NC/2 - k])) w^{-k}    -> odd samples
+// (w = exp(-2 pi i / NC); task 0 owns the packed real bins: slots 0 and NC/4).  Against the
+// shuffle form (split_forward / split_inverse): no SHFL, no per-lane role selects, the
+// same FP64 work, NC/4 block-product tasks of two slots each -- one round over the
+// work warps at the benchmark size instead of two uneven ones.
+// Spectrum layout per node (double2 units): [(2 j + t) P + a], j < NC/4: entry j of the
+// even (t = 0) / odd (t = 1) half-spectrum of sequence a; entry 0 packs the two real bins.
+template <typename Cfg>
+__device__ __noinline__ void fft_f8(const double* __restrict__ U, double* __restrict__ W,
+                                    const int warp, const int lane) {
+    constexpr int NC = Cfg::NC, P = Cfg::P, H = Cfg::H, Q = Cfg::Q, SU = Cfg::SU, SW = Cfg::SW;
+    constexpr int NN = Cfg::NN;
+    if (warp >= Cfg::WORK_WARPS) return;                        // warp-uniform
+    const int n0 = (warp * NN) / Cfg::WORK_WARPS;
+    const int nw = ((warp + 1) * NN) / Cfg::WORK_WARPS - n0;
+    if (nw == 0) return;
+    const int t = lane >> 4, sq = lane & 15;
+    const bool seq_on = sq < nw * P;
+    const int dn = seq_on ? sq / P : 0, a = seq_on ? sq - dn * P : 0;
+    const int node = n0 + dn;
+    double xs[H];
+    const double* src = U + node * SU + a + t * P;
+#pragma unroll
+    for (int mm = 0; mm < H; ++mm) xs[mm] = src[2 * mm * P];
+    double hr[Q], hi[Q];
+    rtfft::Real<NC / 2>::forward(xs, hr, hi);
+    if (seq_on) {
+        double2* const w = reinterpret_cast<double2*>(W + node * SW) + t * P + a;
+#pragma unroll
+        for (int j = 0; j < Q; ++j) w[2 * j * P] = make_double2(hr[j], hi[j]);
+    }
+}
+
+// y[r] = sum_q T[r][q] u[q] (complex); HERM: only the upper triangle of T is read
+template <int P, bool HERM>
+__device__ __forceinline__ void cprod8(const double2* __restrict__ tk, const double2 (&u)[P], double2 (&y)[P]) {
+    if constexpr (HERM) {
+#pragma unroll
+        for (int r = 0; r < P; ++r) {
+            const double2 t = tk[r * P + r];
+            y[r].x = fma(-t.y, u[r].y, t.x * u[r].x);
+            y[r].y = fma(t.y, u[r].x, t.x * u[r].y);
+        }
+#pragma unroll
+        for (int r = 0; r < P; ++r)
+#pragma unroll
+            for (int q = r + 1; q < P; ++q) {
+                const double2 t = tk[r * P + q];
+                y[r].x = fma(t.x, u[q].x, y[r].x);          // y[r] += t u[q]
+                y[r].y = fma(t.x, u[q].y, y[r].y);
+                y[q].x = fma(t.x, u[r].x, y[q].x);          // y[q] += conj(t) u[r]
+                y[q].y = fma(t.x, u[r].y, y[q].y);
+                y[r].x = fma(-t.y, u[q].y, y[r].x);
+                y[r].y = fma(t.y, u[q].x, y[r].y);
+                y[q].x = fma(t.y, u[r].y, y[q].x);
+                y[q].y = fma(-t.y, u[r].x, y[q].y);
+                if (q == P - 1 && (r & 1)) asm volatile("" ::: "memory");   // bounds the table loads in flight
+            }
+    } else {
+#pragma unroll
+        for (int r = 0; r < P; ++r) {
+            double re = tk[r * P].x * u[0].x, im = tk[r * P].x * u[0].y;
+            double r2 = -(tk[r * P].y * u[0].y), i2 = tk[r * P].y * u[0].x;
+#pragma unroll
+            for (int q = 1; q < P; ++q) {
+                const double2 t = tk[r * P + q];
+                re = fma(t.x, u[q].x, re);
+                im = fma(t.x, u[q].y, im);
+                r2 = fma(-t.y, u[q].y, r2);
+                i2 = fma(t.y, u[q].x, i2);
+            }
+            y[r] = make_double2(re + r2, im + i2);
+            asm volatile("" ::: "memory");      // one row of table loads in flight at a time
+        }
+    }
+}
+
+// two real products at once: y.x = sum_q T.x u.x, y.y = sum_q T.y u.y (the packed real bins)
+template <int P, bool HERM>
+__device__ __forceinline__ void rprod8(const double2* __restrict__ tk, const double2 (&u)[P], double2 (&y)[P]) {
+    if constexpr (HERM) {
+#pragma unroll
+        for (int r = 0; r < P; ++r) {
+            const double2 t = tk[r * P + r];
+            y[r] = make_double2(t.x * u[r].x, t.y * u[r].y);
+        }
+#pragma unroll
+        for (int r = 0; r < P; ++r)
+#pragma unroll
+            for (int q = r + 1; q < P; ++q) {
+                const double2 t = tk[r * P + q];
+                y[r].x = fma(t.x, u[q].x, y[r].x);
+                y[r].y = fma(t.y, u[q].y, y[r].y);
+                y[q].x = fma(t.x, u[r].x, y[q].x);
+                y[q].y = fma(t.y, u[r].y, y[q].y);
+            }
+    } else {
+#pragma unroll
+        for (int r = 0; r < P; ++r) {
+            double yr = tk[r * P].x * u[0].x, yi = tk[r * P].y * u[0].y;
+#pragma unroll
+            for (int q = 1; q < P; ++q) {
+                yr = fma(tk[r * P + q].x, u[q].x, yr);
+                yi = fma(tk[r * P + q].y, u[q].y, yi);
+            }
+            y[r] = make_double2(yr, yi);
+            asm volatile("" ::: "memory");
+        }
+    }
+}
+
+template <typename Cfg, bool HERM>
+__device__ __noinline__ void mult8(double* __restrict__ W, const double2* __restrict__ Ts, const int warp_u,
+                                   const int lane) {
+    constexpr int NC = Cfg::NC, P = Cfg::P, NN = Cfg::NN, SW = Cfg::SW, H = Cfg::H, Q = Cfg::Q;
+    constexpr int WW = Cfg::WORK_WARPS;
+    static_assert(NN <= 32, "one lane per spatial node");
+    if (warp_u >= WW) return;
+    const bool on = lane < NN;
+    double2* const wn = reinterpret_cast<double2*>(W) + (on ? lane : 0) * (SW / 2);
+#pragma unroll 1
+    for (int k = warp_u; k < Q; k += WW) {                      // warp-uniform
+        double2* const we = wn + 2 * k * P;                     // even entries [a]; odd entries at + P
+        double2 ua[P], ub[P];
+        if (k == 0) {
+            // slot 0 = (X[0], X[NC/2]) = (E0 + O0, E0 - O0); slot NC/4 = 2 X[NC/4] = (2 E[NC/4], -2 O[NC/4])
+#pragma unroll
+            for (int a = 0; a < P; ++a) {
+                const double2 e = we[a], o = we[P + a];
+                ua[a] = make_double2(e.x + o.x, e.x - o.x);
+                ub[a] = make_double2(2.0 * e.y, -2.0 * o.y);
+            }
+            double2 y0[P], yq[P];
+            rprod8<P, HERM>(Ts, ua, y0);
+            asm volatile("" ::: "memory");
+            cprod8<P, HERM>(Ts + Q * P * P, ub, yq);
+            if (on) {
+#pragma unroll
+                for (int a = 0; a < P; ++a) {
+                    we[a] = make_double2(y0[a].x + y0[a].y, 2.0 * yq[a].x);
+                    we[P + a] = make_double2(y0[a].x - y0[a].y, -2.0 * yq[a].y);
+                }
+            }
+        } else {
+            const double c = c_fft_cos[k * (64 / NC)], s = c_fft_sin[k * (64 / NC)];   // w^k = c - i s
+#pragma unroll
+            for (int a = 0; a < P; ++a) {
+                const double2 e = we[a], o = we[P + a];
+                const double wr = fma(c, o.x, s * o.y), wi = fma(c, o.y, -(s * o.x));
+                ua[a] = make_double2(e.x + wr, e.y + wi);
+                ub[a] = make_double2(e.x - wr, wi - e.y);
+            }
+            double2 ya[P];
+            cprod8<P, HERM>(Ts + k * P * P, ua, ya);
+            asm volatile("" ::: "memory");      // keeps the second block's table loads (and their registers) behind the first product
+            // second product row by row (all P entries of a row are read even when the block is
+            // Hermitian), each row combined with ya and stored at once: ya, ub and four
+            // accumulators are live instead of two whole result vectors
+            const double2* __restrict__ tb = Ts + (H - k) * P * P;
+#pragma unroll
+            for (int r = 0; r < P; ++r) {
+                double re = tb[r * P].x * ub[0].x, im = tb[r * P].x * ub[0].y;
+                double r2 = -(tb[r * P].y * ub[0].y), i2 = tb[r * P].y * ub[0].x;
+#pragma unroll
+                for (int q = 1; q < P; ++q) {
+                    const double2 t = tb[r * P + q];
+                    re = fma(t.x, ub[q].x, re);
+                    im = fma(t.x, ub[q].y, im);
+                    r2 = fma(-t.y, ub[q].y, r2);
+                    i2 = fma(t.y, ub[q].x, i2);
+                }
+                const double ybx = re + r2, yby = im + i2;
+                const double dr = ya[r].x - ybx, di = ya[r].y + yby;
+                if (on) {
+                    we[r] = make_double2(ya[r].x + ybx, ya[r].y - yby);
+                    we[P + r] = make_double2(fma(dr, c, -(di * s)), fma(dr, s, di * c));
+                }
+                asm volatile("" ::: "memory");  // one row of table loads in flight at a time
+            }
+        }
+    }
+}
+
+template <typename Cfg>
+__device__ __noinline__ void fft_i8(double* __restrict__ W, const int warp, const int lane) {
+    constexpr int NC = Cfg::NC, P = Cfg::P, H = Cfg::H, Q = Cfg::Q, SW = Cfg::SW;
+    constexpr int NN = Cfg::NN;
+    if (warp >= Cfg::WORK_WARPS) return;                        // warp-uniform
+    const int n0 = (warp * NN) / Cfg::WORK_WARPS;
+    const int nw = ((warp + 1) * NN) / Cfg::WORK_WARPS - n0;
+    if (nw == 0) return;
+    const int t = lane >> 4, sq = lane & 15;
+    const bool seq_on = sq < nw * P;
+    const int dn = seq_on ? sq / P : 0, a = seq_on ? sq - dn * P : 0;
+    const int node = n0 + dn;
+    const double2* const w = reinterpret_cast<const double2*>(W + node * SW) + t * P + a;
+    double hr[Q], hi[Q];
+#pragma unroll
+    for (int j = 0; j < Q; ++j) {
+        const double2 v = w[2 * j * P];
+        hr[j] = v.x;
+        hi[j] = v.y;
+    }
+    __syncwarp();                                               // the real rows overwrite the spectrum
+    double xs[H];
+    rtfft::Real<NC / 2>::inverse(hr, hi, xs);
+    if (seq_on) {
+        double* dst = W + n0 * SW + dn * Cfg::SWR + a + t * P;      // real-row layout, see Circ7Cfg::wrow
+#pragma unroll
+        for (int mm = 0; mm < H; ++mm) dst[2 * mm * P] = xs[mm];
+    }
+}
+
+// barrier among the work warps (all warps when the block has no spare producer warp)
+template <typename Cfg>
+__device__ __forceinline__ void work_sync(const int warp) {
+    if constexpr (Cfg::WORK_WARPS < Cfg::NWARPS) {
+        if (warp < Cfg::WORK_WARPS) asm volatile("bar.sync 1, %0;\n" ::"n"(Cfg::WORK_WARPS * 32) : "memory");
+    } else {
+        __syncthreads();
+    }
+}
+
 template <int N, int NC, int P>
 __global__ void __launch_bounds__(Circ7Cfg<N, NC, P>::THREADS, Circ7Cfg<N, NC, P>::MINB)
 k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int sg, unsigned terms,
               int interior_only, int herm, const double* __restrict__ x, const double* __restrict__ ghost,
               double* __restrict__ y, const __grid_constant__ CircTab7<Circ7Cfg<N, NC, P>> T,
               const int n_free, const unsigned* __restrict__ halo_flag, const unsigned halo_epoch,
-              const int* __restrict__ resume_in, int* __restrict__ resume_out) {
+              const int* __restrict__ resume_in, int* __restrict__ resume_out, const int mode) {
     using Cfg = Circ7Cfg<N, NC, P>;
+    const bool eo = mode & 1, inner_fast = (mode & 2) != 0;
     constexpr int NN = Cfg::NN, NT = Cfg::NT, NTP = Cfg::NTP;
     constexpr int SU = Cfg::SU, THREADS = Cfg::THREADS;
     extern __shared__ __align__(16) double smem7[];
@@ -707,14 +940,28 @@ k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int 
         phase ^= 1u << cur;
         const double* U = Ub + cur * Cfg::U_DOUBLES;
         if (terms & RTB200_TERM_SCAT) {
-            fft_f7<Cfg>(U, W, warp, lane);
-            __syncthreads();
-            if (herm)
-                mult7_herm<Cfg>(W, reinterpret_cast<const double2*>(Ts), __shfl_sync(0xffffffffu, warp, 0), lane);
-            else
-                mult7<Cfg>(W, reinterpret_cast<const double2*>(Ts), __shfl_sync(0xffffffffu, warp, 0), lane);
-            __syncthreads();
-            fft_i7<Cfg>(W, warp, lane);
+            if (eo) {            // E/O form: the radix-2 stage across the lane pair lives in the block product
+                // The barriers between F, M and I only concern the work warps: a named barrier keeps
+                // the producer warp (bulk-copy issue, metadata loads from global memory) out of them,
+                // so that nobody waits for its latencies before the streaming phase.
+                fft_f8<Cfg>(U, W, warp, lane);
+                work_sync<Cfg>(warp);
+                if (herm)
+                    mult8<Cfg, true>(W, reinterpret_cast<const double2*>(Ts), __shfl_sync(0xffffffffu, warp, 0), lane);
+                else
+                    mult8<Cfg, false>(W, reinterpret_cast<const double2*>(Ts), __shfl_sync(0xffffffffu, warp, 0), lane);
+                work_sync<Cfg>(warp);
+                fft_i8<Cfg>(W, warp, lane);
+            } else {             // shuffle form (RTB200_CIRC7_EO=0)
+                fft_f7<Cfg>(U, W, warp, lane);
+                __syncthreads();
+                if (herm)
+                    mult7_herm<Cfg>(W, reinterpret_cast<const double2*>(Ts), __shfl_sync(0xffffffffu, warp, 0), lane);
+                else
+                    mult7<Cfg>(W, reinterpret_cast<const double2*>(Ts), __shfl_sync(0xffffffffu, warp, 0), lane);
+                __syncthreads();
+                fft_i7<Cfg>(W, warp, lane);
+            }
             __syncthreads();
         }
 
@@ -724,7 +971,13 @@ k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int 
             const double* coef_s = coefb + cur * Cfg::COEF_DOUBLES;
             if (th < NT && tid < 2 * Cfg::NTW) {
                 const double* ws = (terms & RTB200_TERM_SCAT) ? W + th : nullptr;
-                if (full) {
+                if (full && inner_fast && cm.bdry == 0) {
+                    // no face on the domain boundary: every inflow face has a neighbour, no row is masked
+                    if (half == 0)
+                        stream7<N, 0, true, Cfg, true>(cm, coef_s, tab, th, U, ws, terms, interior_only, x, ghost, y);
+                    else
+                        stream7<N, 1, true, Cfg, true>(cm, coef_s, tab, th, U, ws, terms, interior_only, x, ghost, y);
+                } else if (full) {
                     if (half == 0)
                         stream7<N, 0, true, Cfg>(cm, coef_s, tab, th, U, ws, terms, interior_only, x, ghost, y);
                     else

@@ -186,6 +186,10 @@ extern "C" int rtb200_set_mesh(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
         ctx->use_circ = !(env && env[0] == '1');
         const char* cv = getenv("RTB200_CIRC_VERSION");
         if (cv && cv[0] == '6') ctx->circ_version = 6;
+        const char* eo = getenv("RTB200_CIRC7_EO");
+        ctx->circ_eo = !(eo && eo[0] == '0');
+        const char* inr = getenv("RTB200_CIRC7_INNER");
+        ctx->circ_inner = !(inr && inr[0] == '0');
         const char* hs = getenv("RTB200_HP_STREAM");
         ctx->hp_node_stream = hs && strcmp(hs, "node") == 0;
         const char* hk = getenv("RTB200_HP_KERNEL");

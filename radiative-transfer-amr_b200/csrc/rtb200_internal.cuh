@@ -88,6 +88,8 @@ struct rtb200_ctx {
     const double* circ_pool_dev = nullptr;
     bool use_circ = true;          // RTB200_DENSE_SCATTERING=1 in the environment disables it
     int circ_version = 7;          // RTB200_CIRC_VERSION=6 selects the one-block-per-column kernel
+    int circ_eo = 1;               // RTB200_CIRC7_EO=0: shuffle form of the split transforms in k_apply_circ7
+    int circ_inner = 1;            // RTB200_CIRC7_INNER=0: no specialised streaming phase for columns off the boundary
     bool use_hp = true;            // RTB200_HP_KERNEL=old keeps k_apply for every dense column
     bool hp_node_stream = false;   // RTB200_HP_STREAM=node: node-parallel streaming phase of k_apply
     int64_t launches = 0;
