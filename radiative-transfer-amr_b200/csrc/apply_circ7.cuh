@@ -914,10 +914,10 @@ k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int 
     const int half = tid >= Cfg::NTW ? 1 : 0;
     const int th = tid - half * Cfg::NTW;
     int cur = 0, ms = 0;
-    bool halo_ok = false;
+    int n_wait = n_free;     // first position that still has to check the halo flag (ncols once it was seen)
     unsigned phase = 0;      // bit b: parity of the next completion of buffer b
     for (; it < ncols; it += stride) {
-        if (it >= n_free && !halo_ok) {
+        if (it >= n_wait) {
             if (tid == 0) {
                 unsigned seen;
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(halo_flag) : "memory");
@@ -928,7 +928,7 @@ k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int 
                 mbar_wait(&s_bar[cur], (phase >> cur) & 1u);     // the copy of this column is in flight
                 break;
             }
-            halo_ok = true;
+            n_wait = ncols;
         }
         __syncthreads();     // everybody is done with the previous column (U[cur ^ 1], W are free)
         const int ms1 = ms == 2 ? 0 : ms + 1, ms2 = ms1 == 2 ? 0 : ms1 + 1;
