@@ -56,8 +56,6 @@ struct SweepState {
     SweepTab tab{};
     std::vector<void*> allocs;
     std::vector<int32_t> lvl_start;   // [n_levels * SW_NCLS + 1] ranges in items_dev: (level, kernel class)
-    std::vector<int32_t> lvl_as;      // [n_levels * SW_NCLS] angle slots per block of k_pc_sweep_mt (max angles per element, rounded)
-    bool mt_attr_set = false;
     int32_t* items_dev = nullptr;     // (column << 2 | quadrant), level after level
     int64_t n_items = 0;
     int block = 64;
@@ -324,242 +322,6 @@ k_pc_sweep(DevMesh m, SweepTab st, const int32_t* __restrict__ items, int couple
     sweep_element<N>(m, st, item >> 2, item & 3, couple, ncorr, r, z);
 }
 
-
-// ---- N threads per (column, angle): k_pc_sweep_mt ------------------------------------------- //
-// The single-thread element solve above is one long dependent FP64 chain (~12 n^3 FMAs plus
-// n_corr repeats), and a sweep is as slow as the chain of its n_levels launches.  Here the n
-// threads (al = 0 .. n-1) of an angle split every contraction of the fast diagonalisation:
-//   thread i   : row i of the right-hand side (loads r, inflow flux of the upwind columns)
-//   thread al  : spectral row al:  t1[j] = sum_i Lx[al][i] b[i][j],  t2 = (Ly t1) / den,  t1' = Vy t2
-//   thread i   : row i of the result:  z[i][j] += Re sum_al Vx[i][al] t1'_al[j]
-// with the rows exchanged through shared memory (b, z: n x n doubles; t1': n x n complex per
-// angle) -- ~n times shorter per-thread chains, n times more threads per level.  Same arithmetic
-// as sweep_element (sums in the same order), nx == ny == N only.
-template <int N>
-__device__ __forceinline__ void face_flux(const DevMesh& m, const int c, const int F, const int th,
-                                          const int cell, const int rr, const int nth0, const double wF,
-                                          const double half, const double* wq, const double* z,
-                                          double (&fa)[N]) {
-#pragma unroll
-    for (int p = 0; p < N; ++p) fa[p] = 0.0;
-    for (int slot = 0; slot < 2; ++slot) {
-        const int fidx = c * 8 + F * 2 + slot;
-        if (m.face_nbr[fidx] < 0) continue;          // none / other rank / wrap: lagged
-        const double* src = z + m.face_base[fidx];
-        const int rs = m.face_rstride[fidx];
-        const int eo = m.face_exy[fidx];
-        const int ao = m.face_acpl[fidx];
-        if (eo < 0 && ao < 0) {
-            const double f = half * wF;
-#pragma unroll
-            for (int p = 0; p < N; ++p) fa[p] = f * wq[p] * src[(int64_t)p * rs + th];
-            continue;
-        }
-        const int n1 = m.face_n1[fidx];
-        for (int j1 = 0; j1 < n1; ++j1) {
-            double tmp;
-            if (ao < 0) {
-                tmp = wF * src[(int64_t)j1 * rs + th];
-            } else {
-                const int32_t* __restrict__ acp = m.acpl_pool + ao + cell * 6;
-                tmp = 0.0;
-                for (int k = 0; k < 2; ++k) {
-                    const int n1t = acp[k * 3 + 2];
-                    if (n1t == 0) continue;
-                    const double* __restrict__ eth = m.eth_pool + acp[k * 3] + rr;
-                    const double* tr = src + (int64_t)j1 * rs + acp[k * 3 + 1];
-                    for (int a = 0; a < n1t; ++a) tmp = fma(eth[a * nth0], tr[a], tmp);
-                }
-            }
-            tmp *= half;
-            if (eo < 0) {
-#pragma unroll
-                for (int p = 0; p < N; ++p)
-                    if (p == j1) fa[p] = fma(wq[p], tmp, fa[p]);
-            } else {
-                const double* __restrict__ E = m.exy_pool + eo;
-#pragma unroll
-                for (int p = 0; p < N; ++p) fa[p] = fma(E[j1 * N + p], tmp, fa[p]);
-            }
-        }
-    }
-}
-
-// one fast-diagonalisation solve, spread over the N threads of an angle (see above).
-//   brow: this thread's row of the right-hand side; zrow (+)= this thread's row of the solution
-//   Bs [N][N] doubles, Cs [N][N] double2: the angle's exchange buffers
-template <int N, bool ACC>
-__device__ __forceinline__ void fd_solve_mt(const int al, const Fd1 fx, const Fd1 fy, const double kbwt,
-                                            const double ax, const double ay, const double (&brow)[N],
-                                            double (&zrow)[N], double* Bs, double2* Cs) {
-#pragma unroll
-    for (int j = 0; j < N; ++j) Bs[al * N + j] = brow[j];
-    __syncthreads();
-    double2 t1[N], t2[N];
-#pragma unroll
-    for (int j = 0; j < N; ++j) t1[j] = make_double2(0.0, 0.0);
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        const double2 l = __ldg(&fx.L[al * N + i]);
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-            const double b = Bs[i * N + j];
-            t1[j].x = fma(l.x, b, t1[j].x);
-            t1[j].y = fma(l.y, b, t1[j].y);
-        }
-    }
-    const double2 lx = __ldg(&fx.lam[al]);
-#pragma unroll
-    for (int be = 0; be < N; ++be) {
-        double2 sacc = make_double2(0.0, 0.0);
-#pragma unroll
-        for (int j = 0; j < N; ++j) sacc = cfma(__ldg(&fy.L[be * N + j]), t1[j], sacc);
-        const double2 ly = __ldg(&fy.lam[be]);
-        const double dr = fma(ax, lx.x, fma(ay, ly.x, kbwt));
-        const double di = fma(ax, lx.y, ay * ly.y);
-        const double inv = 1.0 / fma(dr, dr, di * di);
-        t2[be] = make_double2((sacc.x * dr + sacc.y * di) * inv, (sacc.y * dr - sacc.x * di) * inv);
-    }
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-        double2 sacc = make_double2(0.0, 0.0);
-#pragma unroll
-        for (int be = 0; be < N; ++be) sacc = cfma(__ldg(&fy.V[j * N + be]), t2[be], sacc);
-        Cs[al * N + j] = sacc;
-    }
-    __syncthreads();
-    // row i = al of the result: z[i][j] (+)= sum_al' Re(Vx[i][al'] t1'_al'[j]), al' ascending
-    if (!ACC) {
-#pragma unroll
-        for (int j = 0; j < N; ++j) zrow[j] = 0.0;
-    }
-#pragma unroll
-    for (int a2 = 0; a2 < N; ++a2) {
-        const double2 v = __ldg(&fx.V[al * N + a2]);
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-            const double2 t = Cs[a2 * N + j];
-            zrow[j] = fma(v.x, t.x, fma(-v.y, t.y, zrow[j]));
-        }
-    }
-}
-
-// Block = one element (column, quadrant): blockDim.x = N * AS threads, thread = (row i = tid / AS,
-// angle slot = tid % AS): the threads of a warp hold consecutive angles (coalesced r / z rows).
-__host__ __device__ constexpr int sw_as_max(int n) { return n <= 4 ? 64 : 48; }   // angle slots per block
-template <int N>
-__global__ void __launch_bounds__(N * sw_as_max(N), N <= 5 ? 2 : 1)
-k_pc_sweep_mt(DevMesh m, SweepTab st, const int32_t* __restrict__ items, int couple, int ncorr, int AS,
-              const double* __restrict__ r, double* z) {
-    extern __shared__ __align__(16) double sw_smem[];
-    const int item = items[blockIdx.x];
-    const int c = item >> 2, q = item & 3;
-    const int i = threadIdx.x / AS, slot = threadIdx.x - i * AS;
-    double* const Bs = sw_smem + (size_t)slot * (4 * N * N);          // [N][N] rhs rows
-    double* const Zs = Bs + N * N;                                    // [N][N] solution rows
-    double2* const Cs = reinterpret_cast<double2*>(Bs + 2 * N * N);   // [N][N] complex
-    const int sg = m.col_sig[c];
-    const int nt = m.sig_nt[sg], ntp = m.sig_ntp[sg];
-    const int64_t tp0 = m.sig_th0[sg];
-    const int64_t off = m.col_slab_off[c];
-    const int bdry = m.col_bdry[c];
-    const double hdx = 0.5 * m.col_dx[c], hdy = 0.5 * m.col_dy[c];
-    const double* wq = c_w + N * RT_MAXN;
-    const double* Sm = c_s + N * RT_MAXN * RT_MAXN;
-    const double* __restrict__ mk = m.coef + m.col_coef_off[c];
-    const double kbar = st.col_kbar[c];
-    const int q0 = st.sig_qth0[sg * 5 + q], nq = st.sig_qth0[sg * 5 + q + 1] - q0;
-
-    if (q == 0 && ntp > nt)                                 // pad entry of an odd row length
-        for (int n = threadIdx.x; n < N * N; n += blockDim.x) z[off + (int64_t)n * ntp + nt] = 0.0;
-
-    for (int t0 = 0; t0 < nq; t0 += AS) {                   // block-uniform trip count (barriers inside)
-        const int t = t0 + slot;
-        const bool on = t < nq;
-        const int th = on ? st.qth_pool[q0 + t] : st.qth_pool[q0];
-        const int bits = m.th_bits[tp0 + th];
-        const double wt = m.th_wt[tp0 + th], ct = m.th_ct[tp0 + th], sn = m.th_st[tp0 + th];
-        const bool outx_hi = bits & 1, outy_hi = bits & 2;      // outflow through face 0 / face 1
-        const int Fx = outx_hi ? 2 : 0, Fy = outy_hi ? 3 : 1;   // the two inflow faces
-        const bool mx = (bdry >> Fx) & 1, my = (bdry >> Fy) & 1; // inflow through the domain boundary
-        const int imx = outx_hi ? 0 : N - 1, jmy = outy_hi ? 0 : N - 1;   // inflow end nodes
-
-        double b[N], zz[N];
-#pragma unroll
-        for (int j = 0; j < N; ++j) b[j] = r[off + (int64_t)(i * N + j) * ntp + th];
-
-        // ---- inflow flux of the upwind columns' z (boundary_convection_matrix.py:348-430) ---- //
-        if (couple) {
-            const int cell = m.th_cell[tp0 + th];
-            const int rr = (bits >> 8) & 0xff;
-            const int nth0 = m.cell_nth[m.sig_cell0[sg] + cell];
-            if (!((bdry >> Fy) & 1)) {                          // y-face: b[i][jmy] -= fa[i]
-                const double wF = m.th_wF[Fy * m.n_theta_pool + tp0 + th];
-                const int f0 = c * 8 + Fy * 2;
-                double fi;
-                if (m.face_nbr[f0 + 1] < 0 && m.face_exy[f0] < 0 && m.face_acpl[f0] < 0) {
-                    // one conforming neighbour (the common case): a single trace value
-                    fi = m.face_nbr[f0] < 0 ? 0.0
-                         : (hdx * wF) * wq[i] * z[m.face_base[f0] + (int64_t)i * m.face_rstride[f0] + th];
-                } else {
-                    double fa[N];
-                    face_flux<N>(m, c, Fy, th, cell, rr, nth0, wF, hdx, wq, z, fa);
-                    fi = 0.0;
-#pragma unroll
-                    for (int p = 0; p < N; ++p)
-                        if (p == i) fi = fa[p];
-                }
-#pragma unroll
-                for (int j = 0; j < N; ++j)
-                    if (j == jmy) b[j] -= fi;
-            }
-            if (i == imx && !((bdry >> Fx) & 1)) {              // x-face: b[imx][j] -= fa[j]
-                const double wF = m.th_wF[Fx * m.n_theta_pool + tp0 + th];
-                double fa[N];
-                face_flux<N>(m, c, Fx, th, cell, rr, nth0, wF, hdy, wq, z, fa);
-#pragma unroll
-                for (int j = 0; j < N; ++j) b[j] -= fa[j];
-            }
-        }
-        // inflow-boundary nodes are not unknowns (get_masks.py:80-110)
-#pragma unroll
-        for (int j = 0; j < N; ++j)
-            if ((mx && i == imx) || (my && j == jmy)) b[j] = 0.0;
-
-        // ---- local solve ------------------------------------------------------------ //
-        const Fd1 fx = fd_tab(st, N, (outx_hi ? 0 : 1) + (mx ? 2 : 0));
-        const Fd1 fy = fd_tab(st, N, (outy_hi ? 0 : 1) + (my ? 2 : 0));
-        const double ax = hdy * ct, ay = hdx * sn, kbwt = kbar * wt;
-        fd_solve_mt<N, false>(i, fx, fy, kbwt, ax, ay, b, zz, Bs, Cs);
-        for (int it = 0; it < ncorr; ++it) {
-            // res = b - A_loc zz with the true nodal extinction (row i; needs the other rows of zz)
-#pragma unroll
-            for (int j = 0; j < N; ++j) Zs[i * N + j] = zz[j];
-            __syncthreads();
-            double res[N];
-            const double ox = outx_hi ? ax : -ax, oy = outy_hi ? ay : -ay;   // |.|: outflow weights
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                double sx = 0.0, sy = 0.0;
-#pragma unroll
-                for (int k = 0; k < N; ++k) sx = fma(Sm[i * RT_MAXN + k], Zs[k * N + j], sx);
-#pragma unroll
-                for (int k = 0; k < N; ++k) sy = fma(Sm[j * RT_MAXN + k], zz[k], sy);
-                double v = mk[i * N + j] * wt * zz[j] - (wq[j] * ax * sx + wq[i] * ay * sy);
-                if (i == (outx_hi ? N - 1 : 0)) v = fma(wq[j] * ox, zz[j], v);
-                if (j == (outy_hi ? N - 1 : 0)) v = fma(wq[i] * oy, zz[j], v);
-                res[j] = ((mx && i == imx) || (my && j == jmy)) ? 0.0 : b[j] - v;
-            }
-            fd_solve_mt<N, true>(i, fx, fy, kbwt, ax, ay, res, zz, Bs, Cs);
-        }
-        if (on) {
-#pragma unroll
-            for (int j = 0; j < N; ++j) z[off + (int64_t)(i * N + j) * ntp + th] = zz[j];
-        }
-        __syncthreads();        // the exchange buffers are rewritten by the next chunk of angles
-    }
-}
-
 constexpr int SW_NCLS = 6;                         // kernel classes: nx == ny == 2..6, else generic
 __host__ __device__ inline int sweep_class(int nx, int ny) { return (nx == ny && nx >= 2 && nx <= 6) ? nx - 1 : 0; }
 
@@ -673,16 +435,6 @@ int build_schedule(rtb200_ctx* ctx, SweepState* S) {
                 if (--indeg[adj[e]] == 0) nxt.push_back(adj[e]);
         cur.swap(nxt);
     }
-    // angle slots per block of the multi-thread kernel: the largest quadrant of the launch's elements
-    S->lvl_as.assign(S->lvl_start.size() - 1, 8);
-    for (size_t l = 0; l + 1 < S->lvl_start.size(); ++l) {
-        int mq = 1;
-        for (int32_t e = S->lvl_start[l]; e < S->lvl_start[l + 1]; ++e) {
-            const int sgc = ctx->h_col_sig[order[e] >> 2], qq = order[e] & 3;
-            mq = std::max(mq, qth0[sgc * 5 + qq + 1] - qth0[sgc * 5 + qq]);
-        }
-        S->lvl_as[l] = std::min(sw_as_max((int)(l % SW_NCLS) + 1), (mq + 7) / 8 * 8);
-    }
     if ((int64_t)order.size() != ni)
         return rt_fail(ctx, RTB200_EUNSUPPORTED,
                        "transport preconditioner: the upwind dependency graph of the columns has a cycle");
@@ -746,38 +498,11 @@ int rt_sweep_apply(rtb200_ctx* ctx, int pc_type, const double* r, double* z, cud
     // one launch per (level, kernel class); the element-wise block-Jacobi has no coupling, so all
     // levels of a class could run at once -- they are launched back to back on the same stream
     const int couple = pc_type == RTB200_PC_SWEEP ? 1 : 0;
-    // n threads per (column, angle) (k_pc_sweep_mt) unless RTB200_PC_SWEEP_MT=0
-    const char* mte = getenv("RTB200_PC_SWEEP_MT");
-    const bool mt = !(mte && mte[0] == '0');
-    if (mt && !S->mt_attr_set) {
-        const int big = 64 * 4 * 36 * (int)sizeof(double);
-        RT_CUDA(ctx, cudaFuncSetAttribute(k_pc_sweep_mt<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        RT_CUDA(ctx, cudaFuncSetAttribute(k_pc_sweep_mt<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        RT_CUDA(ctx, cudaFuncSetAttribute(k_pc_sweep_mt<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        RT_CUDA(ctx, cudaFuncSetAttribute(k_pc_sweep_mt<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        RT_CUDA(ctx, cudaFuncSetAttribute(k_pc_sweep_mt<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        S->mt_attr_set = true;
-    }
     for (size_t l = 0; l + 1 < S->lvl_start.size(); ++l) {
         const int i0 = S->lvl_start[l], cnt = S->lvl_start[l + 1] - i0;
         if (cnt == 0) continue;
         const int32_t* it = S->items_dev + i0;
 #define SW_LAUNCH(N_) k_pc_sweep<N_><<<cnt, S->block, 0, st>>>(ctx->dm, S->tab, it, couple, ncorr, r, z)
-#define SW_LAUNCH_MT(N_)                                                                            \
-    k_pc_sweep_mt<N_><<<cnt, N_ * as, sizeof(double) * 4 * N_ * N_ * as, st>>>(ctx->dm, S->tab, it, couple, \
-                                                                                 ncorr, as, r, z)
-        const int as = S->lvl_as[l];
-        if (mt && l % SW_NCLS != 0) {
-            switch ((int)(l % SW_NCLS)) {
-                case 1: SW_LAUNCH_MT(2); break;
-                case 2: SW_LAUNCH_MT(3); break;
-                case 3: SW_LAUNCH_MT(4); break;
-                case 4: SW_LAUNCH_MT(5); break;
-                default: SW_LAUNCH_MT(6); break;
-            }
-            ctx->launches++;
-            continue;
-        }
         switch ((int)(l % SW_NCLS)) {
             case 1: SW_LAUNCH(2); break;
             case 2: SW_LAUNCH(3); break;
@@ -787,7 +512,6 @@ int rt_sweep_apply(rtb200_ctx* ctx, int pc_type, const double* r, double* z, cud
             default: SW_LAUNCH(0); break;
         }
 #undef SW_LAUNCH
-#undef SW_LAUNCH_MT
         ctx->launches++;
     }
     RT_CUDA(ctx, cudaGetLastError());
