@@ -218,12 +218,33 @@ __device__ __forceinline__ void split_inverse(const double2 (&ia)[NC / 8], const
 // FULL: all four terms (the solver's call); the term tests are compiled out.
 // Order: neighbour-trace loads are issued first and consumed last (L2 latency hidden
 // behind the two derivative passes over shared memory).
+// Kernel arguments the streaming phase needs, kept in shared memory: as parameters of the
+// out-of-line stream7 they would travel through the stack (more arguments than the ABI has
+// registers for), and the streaming phase would wait for those local-memory loads behind its own
+// global trace loads (13 % of its stall samples, profiles/r02_q_*).
+struct StreamArgs7 {
+    const double* x;
+    const double* ghost;
+    double* y;
+    unsigned terms;
+    int interior_only;
+};
+
 template <int N, int HALF, bool FULL, typename Cfg, bool INNER = false>
-__device__ __noinline__ void stream7(
-    const ColMeta& cm, const double* __restrict__ coef_s, const double* __restrict__ tab,
-    const int th, const double* __restrict__ us, const double* __restrict__ ws, const unsigned terms,
-    const int interior_only, const double* __restrict__ x, const double* __restrict__ ghost,
-    double* __restrict__ y) {
+__device__ __noinline__ void stream7(const ColMeta& cm, const int th, const int cur, const StreamArgs7& sa) {
+    // the block's dynamic shared memory (layout: k_apply_circ7), addressed from its base so that
+    // the call needs four argument registers
+    extern __shared__ __align__(16) double smem7[];
+    const double* __restrict__ us = smem7 + cur * Cfg::U_DOUBLES;
+    const double* __restrict__ tab = smem7 + 2 * Cfg::U_DOUBLES + Cfg::W_DOUBLES + Cfg::T_DOUBLES;
+    const double* __restrict__ coef_s = tab + Cfg::TAB_DOUBLES + cur * Cfg::COEF_DOUBLES;
+    const unsigned terms = sa.terms;
+    const double* __restrict__ ws = (FULL || (terms & RTB200_TERM_SCAT)) ? smem7 + 2 * Cfg::U_DOUBLES + th : nullptr;
+    const int interior_only = sa.interior_only;
+    const double* __restrict__ x = sa.x;
+    const double* __restrict__ ghost = sa.ghost;
+    __builtin_assume(__isGlobal(x));        // read back from shared memory: tell the compiler the state space
+    __builtin_assume(__isGlobal(ghost));
     constexpr int NN = N * N, NT = Cfg::NT, SU = Cfg::SU, SW = Cfg::SW, NTP = Cfg::NTP;
     constexpr int NA = Cfg::NA;
 #define RT_MINE(i, j) (HALF == 0 ? ((i) * N + (j) < NA) : ((i) * N + (j) >= NA))
@@ -246,6 +267,7 @@ __device__ __noinline__ void stream7(
     {
         const long long base = cm.face_base[2 * Fx];
         const double* __restrict__ src = (base >= 0 ? x + base : ghost + (-(base + 2))) + th;
+        __builtin_assume(__isGlobal(src));
         const int rs = cm.rs[2 * Fx];
 #pragma unroll
         for (int q = 0; q < N; ++q) tx[q] = in_x ? src[(int64_t)q * rs] : 0.0;
@@ -253,6 +275,7 @@ __device__ __noinline__ void stream7(
     {
         const long long base = cm.face_base[2 * Fy];
         const double* __restrict__ src = (base >= 0 ? x + base : ghost + (-(base + 2))) + th;
+        __builtin_assume(__isGlobal(src));
         const int rs = cm.rs[2 * Fy];
 #pragma unroll
         for (int q = 0; q < N; ++q)
@@ -341,6 +364,9 @@ __device__ __noinline__ void stream7(
     const bool msk = !INNER && interior_only != 0;
     const bool m0 = msk && (bdry & 1) && (bits & 16), m1 = msk && (bdry & 2) && (bits & 32);
     const bool m2 = msk && (bdry & 4) && (bits & 64), m3 = msk && (bdry & 8) && (bits & 128);
+    asm volatile("" ::: "memory");          // y is fetched here, not at the top (it would be spilled across the phase)
+    double* __restrict__ y = sa.y;
+    __builtin_assume(__isGlobal(y));
     double* yc = y + cm.slab_off + th;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -767,29 +793,15 @@ __device__ __noinline__ void mult8(double* __restrict__ W, const double2* __rest
             double2 ya[P];
             cprod8<P, HERM>(Ts + k * P * P, ua, ya);
             asm volatile("" ::: "memory");      // keeps the second block's table loads (and their registers) behind the first product
-            // second product row by row (all P entries of a row are read even when the block is
-            // Hermitian), each row combined with ya and stored at once: ya, ub and four
-            // accumulators are live instead of two whole result vectors
-            const double2* __restrict__ tb = Ts + (H - k) * P * P;
+            double2 yb[P];
+            cprod8<P, HERM>(Ts + (H - k) * P * P, ub, yb);
 #pragma unroll
             for (int r = 0; r < P; ++r) {
-                double re = tb[r * P].x * ub[0].x, im = tb[r * P].x * ub[0].y;
-                double r2 = -(tb[r * P].y * ub[0].y), i2 = tb[r * P].y * ub[0].x;
-#pragma unroll
-                for (int q = 1; q < P; ++q) {
-                    const double2 t = tb[r * P + q];
-                    re = fma(t.x, ub[q].x, re);
-                    im = fma(t.x, ub[q].y, im);
-                    r2 = fma(-t.y, ub[q].y, r2);
-                    i2 = fma(t.y, ub[q].x, i2);
-                }
-                const double ybx = re + r2, yby = im + i2;
-                const double dr = ya[r].x - ybx, di = ya[r].y + yby;
+                const double dr = ya[r].x - yb[r].x, di = ya[r].y + yb[r].y;
                 if (on) {
-                    we[r] = make_double2(ya[r].x + ybx, ya[r].y - yby);
+                    we[r] = make_double2(ya[r].x + yb[r].x, ya[r].y - yb[r].y);
                     we[P + r] = make_double2(fma(dr, c, -(di * s)), fma(dr, s, di * c));
                 }
-                asm volatile("" ::: "memory");  // one row of table loads in flight at a time
             }
         }
     }
@@ -868,6 +880,8 @@ k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int 
         return;
     }
     __shared__ int s_go;
+    __shared__ StreamArgs7 s_args;
+    if (threadIdx.x == 0) s_args = StreamArgs7{x, ghost, y, terms, interior_only};   // published by the prologue barrier
 
     // ---- prologue: per-angle tables, block spectrum, metadata of the first two columns -- //
     {
@@ -968,25 +982,23 @@ k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int 
         // ---- phase S: streaming terms + scattering combine -> y -------------------- //
         {
             const ColMeta& cm = s_meta[ms].cm;
-            const double* coef_s = coefb + cur * Cfg::COEF_DOUBLES;
             if (th < NT && tid < 2 * Cfg::NTW) {
-                const double* ws = (terms & RTB200_TERM_SCAT) ? W + th : nullptr;
                 if (full && inner_fast && cm.bdry == 0) {
                     // no face on the domain boundary: every inflow face has a neighbour, no row is masked
                     if (half == 0)
-                        stream7<N, 0, true, Cfg, true>(cm, coef_s, tab, th, U, ws, terms, interior_only, x, ghost, y);
+                        stream7<N, 0, true, Cfg, true>(cm, th, cur, s_args);
                     else
-                        stream7<N, 1, true, Cfg, true>(cm, coef_s, tab, th, U, ws, terms, interior_only, x, ghost, y);
+                        stream7<N, 1, true, Cfg, true>(cm, th, cur, s_args);
                 } else if (full) {
                     if (half == 0)
-                        stream7<N, 0, true, Cfg>(cm, coef_s, tab, th, U, ws, terms, interior_only, x, ghost, y);
+                        stream7<N, 0, true, Cfg>(cm, th, cur, s_args);
                     else
-                        stream7<N, 1, true, Cfg>(cm, coef_s, tab, th, U, ws, terms, interior_only, x, ghost, y);
+                        stream7<N, 1, true, Cfg>(cm, th, cur, s_args);
                 } else {
                     if (half == 0)
-                        stream7<N, 0, false, Cfg>(cm, coef_s, tab, th, U, ws, terms, interior_only, x, ghost, y);
+                        stream7<N, 0, false, Cfg>(cm, th, cur, s_args);
                     else
-                        stream7<N, 1, false, Cfg>(cm, coef_s, tab, th, U, ws, terms, interior_only, x, ghost, y);
+                        stream7<N, 1, false, Cfg>(cm, th, cur, s_args);
                 }
             } else if (half == 0 && th < NTP) {             // pad entry of an odd row length
                 double* yc = y + cm.slab_off + th;

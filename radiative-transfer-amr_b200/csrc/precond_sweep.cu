@@ -51,12 +51,31 @@ struct SweepTab {                  // device pointers
     const double* col_kbar;        // [n_col] (dx dy / 4) * mid-range extinction of the column
 };
 
+// Everything a thread needs to know about its (column, quadrant) element, gathered on the host
+// when the schedule is built: ONE load instead of a chain of dependent table look-ups
+// (item -> column -> signature -> ...).
+struct SweepElem {
+    int64_t off;        // col_slab_off
+    int64_t coef_off;   // col_coef_off
+    int64_t tp0;        // sig_th0 of the column's signature
+    int32_t c, q;
+    int32_t nt, ntp;
+    int32_t q0, nq;     // range of the quadrant's angles in qth_pool
+    int32_t bdry, sg;
+    int32_t cell0, nx;
+    int32_t ny, pad;
+    double hdx, hdy;    // dx / 2, dy / 2
+};
+
 struct SweepState {
     bool have_fd = false, have_sched = false, have_coef = false;
     SweepTab tab{};
     std::vector<void*> allocs;
     std::vector<int32_t> lvl_start;   // [n_levels * SW_NCLS + 1] ranges in items_dev: (level, kernel class)
     int32_t* items_dev = nullptr;     // (column << 2 | quadrant), level after level
+    SweepElem* elems_dev = nullptr;   // the same sequence as records
+    uint32_t* pairs_dev = nullptr;    // (element index << 8 | angle index in the quadrant): the flat work list
+    std::vector<int64_t> pair_start;  // [n_levels * SW_NCLS + 1] ranges in pairs_dev
     int64_t n_items = 0;
     int block = 64;
     double rho_max = 0.0;             // max over columns of (kmax - kmin) / (kmax + kmin)
@@ -154,34 +173,38 @@ __device__ __forceinline__ void fd_solve(const int nx, const int ny, const Fd1 f
     }
 }
 
-// One element: column c, quadrant q.  One thread per angle of the quadrant.
-// N > 0: nx == ny == N at compile time; N == 0: any nx, ny <= RT_MAXN (arrays in local memory).
-template <int N>
-__device__ __forceinline__ void sweep_element(const DevMesh& m, const SweepTab& st, const int c,
-                                              const int q, const bool couple, const int ncorr,
-                                              const double* __restrict__ r, double* z) {
+// Column-level context of one (column, quadrant) element.
+struct SweepCol {
+    int c, nx, ny, sg, ntp, bdry, cell0;
+    int64_t tp0, off;
+    double hdx, hdy, kbar;
+    const double* mk;
+};
+
+// One (column, quadrant, angle): right-hand side minus the inflow flux of the upwind columns,
+// local solve, store.  N > 0: nx == ny == N at compile time; N == 0: any nx, ny <= RT_MAXN.
+template <int N, bool CORR = true>
+__device__ __forceinline__ void sweep_angle(const DevMesh& m, const SweepTab& st, const SweepCol& k,
+                                            const int th, const bool couple, const int ncorr_in,
+                                            const double* __restrict__ r, double* z) {
     constexpr int NF = N > 0 ? N : RT_MAXN;
-    const int nx = N > 0 ? N : m.col_nx[c];
-    const int ny = N > 0 ? N : m.col_ny[c];
-    const int sg = m.col_sig[c];
-    const int nt = m.sig_nt[sg], ntp = m.sig_ntp[sg];
-    const int64_t tp0 = m.sig_th0[sg];
-    const int64_t off = m.col_slab_off[c];
-    const int bdry = m.col_bdry[c];
-    const double hdx = 0.5 * m.col_dx[c], hdy = 0.5 * m.col_dy[c];
+    const int c = k.c;
+    const int nx = N > 0 ? N : k.nx;
+    const int ny = N > 0 ? N : k.ny;
+    const int sg = k.sg;
+    const int ntp = k.ntp;
+    const int64_t tp0 = k.tp0;
+    const int64_t off = k.off;
+    const int bdry = k.bdry;
+    const double hdx = k.hdx, hdy = k.hdy;
     const double* wx = c_w + nx * RT_MAXN;
     const double* wy = c_w + ny * RT_MAXN;
     const double* Sx = c_s + nx * RT_MAXN * RT_MAXN;
     const double* Sy = c_s + ny * RT_MAXN * RT_MAXN;
-    const double* __restrict__ mk = m.coef + m.col_coef_off[c];
-    const double kbar = st.col_kbar[c];
-    const int q0 = st.sig_qth0[sg * 5 + q], nq = st.sig_qth0[sg * 5 + q + 1] - q0;
-
-    if (q == 0 && ntp > nt)                                 // pad entry of an odd row length
-        for (int n = threadIdx.x; n < nx * ny; n += blockDim.x) z[off + (int64_t)n * ntp + nt] = 0.0;
-
-    for (int t = threadIdx.x; t < nq; t += blockDim.x) {
-        const int th = st.qth_pool[q0 + t];
+    const double* __restrict__ mk = k.mk;
+    const double kbar = k.kbar;
+    const int ncorr = CORR ? ncorr_in : 0;      // CORR = false: the defect-correction loop is compiled out
+    {
         const int bits = m.th_bits[tp0 + th];
         const double wt = m.th_wt[tp0 + th], ct = m.th_ct[tp0 + th], sn = m.th_st[tp0 + th];
         const bool outx_hi = bits & 1, outy_hi = bits & 2;      // outflow through face 0 / face 1
@@ -200,7 +223,7 @@ __device__ __forceinline__ void sweep_element(const DevMesh& m, const SweepTab& 
         if (couple) {
             const int cell = m.th_cell[tp0 + th];
             const int rr = (bits >> 8) & 0xff;
-            const int nth0 = m.cell_nth[m.sig_cell0[sg] + cell];
+            const int nth0 = m.cell_nth[k.cell0 + cell];
 #pragma unroll
             for (int ff = 0; ff < 2; ++ff) {
                 const int F = ff == 0 ? Fx : Fy;
@@ -314,6 +337,48 @@ __device__ __forceinline__ void sweep_element(const DevMesh& m, const SweepTab& 
     }
 }
 
+// One element: column c, quadrant q.  One thread per angle of the quadrant (generic class).
+template <int N>
+__device__ __forceinline__ void sweep_element(const DevMesh& m, const SweepTab& st, const int c,
+                                              const int q, const bool couple, const int ncorr,
+                                              const double* __restrict__ r, double* z) {
+    const int sg = m.col_sig[c];
+    const int nt = m.sig_nt[sg];
+    SweepCol k;
+    k.c = c; k.nx = m.col_nx[c]; k.ny = m.col_ny[c]; k.sg = sg; k.ntp = m.sig_ntp[sg];
+    k.bdry = m.col_bdry[c]; k.cell0 = m.sig_cell0[sg];
+    k.tp0 = m.sig_th0[sg]; k.off = m.col_slab_off[c];
+    k.hdx = 0.5 * m.col_dx[c]; k.hdy = 0.5 * m.col_dy[c]; k.kbar = st.col_kbar[c];
+    k.mk = m.coef + m.col_coef_off[c];
+    const int q0 = st.sig_qth0[sg * 5 + q], nq = st.sig_qth0[sg * 5 + q + 1] - q0;
+    if (q == 0 && k.ntp > nt)                               // pad entry of an odd row length
+        for (int n = threadIdx.x; n < k.nx * k.ny; n += blockDim.x) z[k.off + (int64_t)n * k.ntp + nt] = 0.0;
+    for (int t = threadIdx.x; t < nq; t += blockDim.x)
+        sweep_angle<N>(m, st, k, st.qth_pool[q0 + t], couple, ncorr, r, z);
+}
+
+// Flat form: the (element, angle) pairs of a level are one work list, one thread each, so that
+// every warp is full whatever the number of angles per quadrant (40 at the benchmark mesh: the
+// one-block-per-element form left 24 of 64 lanes idle).  The element record replaces the
+// column -> signature -> ... look-up chain.
+template <int N, bool CORR>
+__global__ void __launch_bounds__(128, CORR ? 2 : 3)
+k_pc_sweep_flat(DevMesh m, SweepTab st, const SweepElem* __restrict__ elems, const uint32_t* __restrict__ pairs,
+                const int n_pairs, int couple, int ncorr, const double* __restrict__ r, double* z) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_pairs) return;
+    const uint32_t p = pairs[w];
+    const SweepElem el = elems[p >> 8];
+    const int t = (int)(p & 255u);
+    SweepCol k;
+    k.c = el.c; k.nx = el.nx; k.ny = el.ny; k.sg = el.sg; k.ntp = el.ntp; k.bdry = el.bdry; k.cell0 = el.cell0;
+    k.tp0 = el.tp0; k.off = el.off; k.hdx = el.hdx; k.hdy = el.hdy; k.kbar = st.col_kbar[el.c];
+    k.mk = m.coef + el.coef_off;
+    if (t == 0 && el.q == 0 && el.ntp > el.nt)              // pad entry of an odd row length
+        for (int n = 0; n < k.nx * k.ny; ++n) z[k.off + (int64_t)n * k.ntp + el.nt] = 0.0;
+    sweep_angle<N, CORR>(m, st, k, st.qth_pool[el.q0 + t], couple, ncorr, r, z);
+}
+
 template <int N>
 __global__ void __launch_bounds__(64)
 k_pc_sweep(DevMesh m, SweepTab st, const int32_t* __restrict__ items, int couple, int ncorr,
@@ -344,6 +409,16 @@ __global__ void k_col_kbar(DevMesh m, double* __restrict__ kbar, double* __restr
     hi = fmax(hi, 0.0);
     kbar[c] = s * 0.5 * (lo + hi);
     rho[c] = (hi + lo) > 0.0 ? (hi - lo) / (hi + lo) : 0.0;
+}
+
+// pairs[pair0[e] + t] = (e << 8 | t), t < nq of element e
+__global__ void k_fill_pairs(const SweepElem* __restrict__ elems, const int64_t* __restrict__ pair0, const int ne,
+                             uint32_t* __restrict__ pairs) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    const int nq = elems[e].nq;
+    uint32_t* dst = pairs + pair0[e];
+    for (int t = 0; t < nq; ++t) dst[t] = ((uint32_t)e << 8) | (uint32_t)t;
 }
 
 template <typename T>
@@ -444,6 +519,59 @@ int build_schedule(rtb200_ctx* ctx, SweepState* S) {
     const int32_t* d32 = nullptr;
     if ((rc = dev_upload(ctx, S, order, &d32))) return rc;
     S->items_dev = const_cast<int32_t*>(d32);
+    {
+        // element records (see SweepElem) and the flat (element, angle) work list; the tables without
+        // a host copy come back from the device (once per mesh)
+        std::vector<int64_t> slab_off(std::max(nc, 1));
+        std::vector<int32_t> sig_ntp(std::max(n_sig, 1)), sig_cell0(std::max(n_sig, 1));
+        if (nc > 0)
+            RT_CUDA(ctx, cudaMemcpy(slab_off.data(), ctx->dm.col_slab_off, sizeof(int64_t) * nc, cudaMemcpyDeviceToHost));
+        if (n_sig > 0) {
+            RT_CUDA(ctx, cudaMemcpy(sig_ntp.data(), ctx->dm.sig_ntp, sizeof(int32_t) * n_sig, cudaMemcpyDeviceToHost));
+            RT_CUDA(ctx, cudaMemcpy(sig_cell0.data(), ctx->dm.sig_cell0, sizeof(int32_t) * n_sig, cudaMemcpyDeviceToHost));
+        }
+        std::vector<SweepElem> elems(order.size());
+        std::vector<int64_t> pair0(order.size() + 1, 0);       // first pair of every element
+        bool flat_ok = order.size() < (1u << 24);
+        S->pair_start.assign(1, 0);
+        size_t l = 0;
+        for (size_t e = 0; e < order.size(); ++e) {
+            while (l + 1 < S->lvl_start.size() && (int32_t)e >= S->lvl_start[l + 1]) {
+                S->pair_start.push_back(pair0[e]);
+                ++l;
+            }
+            const int c = order[e] >> 2, q = order[e] & 3, sg = ctx->h_col_sig[c];
+            SweepElem& E = elems[e];
+            E.off = slab_off[c];
+            E.coef_off = ctx->h_col_coef_off[c];
+            E.tp0 = ctx->h_sig_th0[sg];
+            E.c = c; E.q = q;
+            E.nt = ctx->h_sig_nt[sg]; E.ntp = sig_ntp[sg];
+            E.q0 = qth0[sg * 5 + q]; E.nq = qth0[sg * 5 + q + 1] - E.q0;
+            E.bdry = ctx->h_col_bdry[c]; E.sg = sg;
+            E.cell0 = sig_cell0[sg]; E.nx = ctx->h_col_nx[c];
+            E.ny = ctx->h_col_ny[c]; E.pad = 0;
+            E.hdx = 0.5 * ctx->h_col_dx[c]; E.hdy = 0.5 * ctx->h_col_dy[c];
+            if (E.nq > 255) flat_ok = false;
+            pair0[e + 1] = pair0[e] + E.nq;
+        }
+        const int64_t n_pairs = pair0[order.size()];
+        while (S->pair_start.size() < S->lvl_start.size()) S->pair_start.push_back(n_pairs);
+        if (flat_ok && !order.empty()) {
+            const SweepElem* de = nullptr;
+            const int64_t* dp0 = nullptr;
+            if ((rc = dev_upload(ctx, S, elems, &de))) return rc;
+            if ((rc = dev_upload(ctx, S, pair0, &dp0))) return rc;
+            S->elems_dev = const_cast<SweepElem*>(de);
+            RT_CUDA(ctx, cudaMalloc((void**)&S->pairs_dev, sizeof(uint32_t) * std::max<int64_t>(n_pairs, 1)));
+            S->allocs.push_back(S->pairs_dev);
+            const int ne = (int)order.size();
+            k_fill_pairs<<<(ne + 255) / 256, 256>>>(de, dp0, ne, S->pairs_dev);   // expanded on the device
+            ctx->launches++;
+            RT_CUDA(ctx, cudaGetLastError());
+            RT_CUDA(ctx, cudaDeviceSynchronize());
+        }
+    }
     if ((rc = dev_upload(ctx, S, qth0, &S->tab.sig_qth0))) return rc;
     if ((rc = dev_upload(ctx, S, pool, &S->tab.qth_pool))) return rc;
     RT_CUDA(ctx, cudaMemcpyToSymbol(c_w, ctx->h_lgl_w.data(), sizeof(double) * ctx->h_lgl_w.size()));
@@ -498,11 +626,39 @@ int rt_sweep_apply(rtb200_ctx* ctx, int pc_type, const double* r, double* z, cud
     // one launch per (level, kernel class); the element-wise block-Jacobi has no coupling, so all
     // levels of a class could run at once -- they are launched back to back on the same stream
     const int couple = pc_type == RTB200_PC_SWEEP ? 1 : 0;
+    // flat (element, angle) work list unless RTB200_PC_SWEEP_FLAT=0 (or an element index / angle
+    // count that does not fit the packed pair)
+    const char* fe = getenv("RTB200_PC_SWEEP_FLAT");
+    const bool flat = S->pairs_dev && !(fe && fe[0] == '0');
     for (size_t l = 0; l + 1 < S->lvl_start.size(); ++l) {
         const int i0 = S->lvl_start[l], cnt = S->lvl_start[l + 1] - i0;
         if (cnt == 0) continue;
         const int32_t* it = S->items_dev + i0;
 #define SW_LAUNCH(N_) k_pc_sweep<N_><<<cnt, S->block, 0, st>>>(ctx->dm, S->tab, it, couple, ncorr, r, z)
+#define SW_LAUNCH_FLAT(N_)                                                                                     \
+    do {                                                                                                       \
+        if (ncorr > 0)                                                                                         \
+            k_pc_sweep_flat<N_, true><<<(np + 127) / 128, 128, 0, st>>>(ctx->dm, S->tab, S->elems_dev,         \
+                                                                       S->pairs_dev + p0, np, couple, ncorr, r, z); \
+        else                                                                                                   \
+            k_pc_sweep_flat<N_, false><<<(np + 127) / 128, 128, 0, st>>>(ctx->dm, S->tab, S->elems_dev,        \
+                                                                        S->pairs_dev + p0, np, couple, 0, r, z);  \
+    } while (0)
+        if (flat && l % SW_NCLS != 0) {
+            const int64_t p0 = S->pair_start[l];
+            const int np = (int)(S->pair_start[l + 1] - p0);
+            if (np > 0) {
+                switch ((int)(l % SW_NCLS)) {
+                    case 1: SW_LAUNCH_FLAT(2); break;
+                    case 2: SW_LAUNCH_FLAT(3); break;
+                    case 3: SW_LAUNCH_FLAT(4); break;
+                    case 4: SW_LAUNCH_FLAT(5); break;
+                    default: SW_LAUNCH_FLAT(6); break;
+                }
+                ctx->launches++;
+            }
+            continue;
+        }
         switch ((int)(l % SW_NCLS)) {
             case 1: SW_LAUNCH(2); break;
             case 2: SW_LAUNCH(3); break;
@@ -512,6 +668,7 @@ int rt_sweep_apply(rtb200_ctx* ctx, int pc_type, const double* r, double* z, cud
             default: SW_LAUNCH(0); break;
         }
 #undef SW_LAUNCH
+#undef SW_LAUNCH_FLAT
         ctx->launches++;
     }
     RT_CUDA(ctx, cudaGetLastError());
