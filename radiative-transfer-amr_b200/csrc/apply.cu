@@ -383,13 +383,35 @@ static int launch_circ(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int int
             int per_sm = 2;                       // persistent grid: every block the SMs can hold
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::THREADS, Cfg::SMEM);
             if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-            const int grid = std::min(count, std::max(per_sm, 1) * ctx->sm_count);
+            // Multi-GPU apply with the halo exchange in flight (n_free < count): the exchange's own
+            // kernels (k_pack, NCCL send / recv) need a few SMs at the same time.  A grid that fills
+            // every SM makes the blocks that do not fit wait for them (~35 us), and with static
+            // column strides the whole apply then ends that much later; leaving ctx->halo_sm_reserve
+            // SMs free costs their share of the throughput instead (RTB200_HALO_SM_RESERVE, default 4).
+            const int sms = (n_free < count || resume) ? std::max(1, ctx->sm_count - ctx->halo_sm_reserve) : ctx->sm_count;
+            const int grid = std::min(count, std::max(per_sm, 1) * sms);
             // resume: 1 = first launch of a split apply (blocks note where they stopped),
             //         2 = second launch (blocks start where the first one stopped)
-            if (resume && (!ctx->halo_resume_dev || grid > RT_HALO_RESUME_SLOTS))
+            if (resume && (!ctx->halo_resume_dev || 2 * grid > RT_HALO_RESUME_SLOTS))
                 return rt_fail(ctx, RTB200_ESTATE, "no resume slots for the split persistent apply");
             if (b.circ_tab_host.size() != sizeof(CircTab7<Cfg>) / sizeof(double))
                 return rt_fail(ctx, RTB200_EINVAL, "circulant table size mismatch");
+            // column-schedule counters of this (column list, stream)
+            unsigned* sched = nullptr;
+            {
+                const auto key = std::make_pair((const void*)b.cols_dev, (void*)st);
+                auto itc = ctx->sched_slots.find(key);
+                if (itc == ctx->sched_slots.end()) {
+                    e = cudaMalloc((void**)&sched, 2 * sizeof(unsigned));
+                    if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaMalloc(schedule counters)");
+                    ctx->allocs.push_back(sched);
+                    e = cudaMemset(sched, 0, 2 * sizeof(unsigned));
+                    if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaMemset(schedule counters)");
+                    ctx->sched_slots[key] = sched;
+                } else {
+                    sched = itc->second;
+                }
+            }
             CircTab7<Cfg> T;                      // 16 M P^2 bytes, passed in the constant bank
             memcpy(&T, b.circ_tab_host.data(), sizeof(T));
             kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(ctx->dm, cols_dev, count, b.circ_sig, terms,
@@ -398,7 +420,7 @@ static int launch_circ(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int int
                                                         halo_epoch,
                                                         resume == 2 ? ctx->halo_resume_dev : nullptr,
                                                         resume == 1 ? ctx->halo_resume_dev : nullptr,
-                                                        ctx->circ_eo | (ctx->circ_inner << 1));
+                                                        resume == 1 ? 8 : 0, sched);
             ctx->launches++;
             e = cudaGetLastError();
             if (e != cudaSuccess) return rt_cuda(ctx, e, "k_apply_circ7 launch");
@@ -550,6 +572,15 @@ int rt_apply_with_halo(rtb200_ctx* ctx, unsigned terms, int interior_only, const
     RT_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_fork, 0));
     rc = rtb200_halo_exchange(ctx, x, (void*)ctx->comm_stream);
     if (rc) return rc;
+    if (ctx->ev_packed) {
+        // The apply waits for the traces to be packed, so that it is released together with the
+        // exchange's send / receive kernel, which sits on a high-priority stream and is placed
+        // first: a persistent grid that has filled the device already would keep that kernel out
+        // until its blocks leave (i.e. until they stop at their ghost-reading columns).  The blocks of
+        // the apply that do not fit next to it start ~35 us late -- harmless with the dynamic
+        // column schedule of k_apply_circ7.
+        RT_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_packed, 0));
+    }
     if (ctx->halo_fused && b.cols_all_dev && b.circ_conforming && b.circ_nc >= 8 && ctx->circ_version >= 7) {
         // ONE persistent pass over all columns, those that read no ghost trace first.  The
         // communication stream raises a flag after the exchange; a block that reaches its first
@@ -564,8 +595,11 @@ int rt_apply_with_halo(rtb200_ctx* ctx, unsigned terms, int interior_only, const
         RT_CUDA(ctx, cudaGetLastError());
         RT_CUDA(ctx, cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
         const int all = b.count_int + b.count_halo;
+        // RTB200_HALO_FORCE_RESUME=1 (tests): the first launch looks for the NEXT epoch, so every block
+        // stops at its first ghost-reading column and the second launch does real work
+        const char* fr = getenv("RTB200_HALO_FORCE_RESUME");
         rc = launch_one_bucket(ctx, b, terms, interior_only, x, y, st, b.cols_all_dev, all, b.count_int,
-                               epoch, 1);
+                               (fr && fr[0] == '1') ? epoch + 1 : epoch, 1);
         cudaStreamWaitEvent(st, ctx->ev_halo, 0);      // always rejoin
         if (rc) return rc;
         return launch_one_bucket(ctx, b, terms, interior_only, x, y, st, b.cols_all_dev, all, all, epoch, 2);
@@ -827,8 +861,11 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
         }
         b.count_int = (int)ci.size();
         b.count_halo = (int)ch.size();
+        if (!ctx->ev_packed) RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_packed, cudaEventDisableTiming));
         if (!ctx->comm_stream) {
-            RT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+            int prio_lo = 0, prio_hi = 0;
+            RT_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            RT_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, prio_hi));
             RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
             if (!ctx->ev_fork) RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
         }
@@ -840,7 +877,9 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
     ctx->overlap_multi = false;
     if (m->n_peer > 0 && !ctx->overlap_ready) {
         if (!ctx->comm_stream) {
-            RT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+            int prio_lo = 0, prio_hi = 0;
+            RT_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            RT_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, prio_hi));
             RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
         }
         if (!ctx->ev_fork) RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));

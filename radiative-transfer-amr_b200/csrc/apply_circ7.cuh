@@ -130,86 +130,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, const uns
         : "memory");
 }
 
-// ---- split real FFT: forward ------------------------------------------------ //
-// xs[m] = x[2 m + t], m < NC/2.  Output: the NC/4 spectrum slots this lane owns, in
-// the slot convention of fft_real.cuh for length NC (slot 0 = (X[0], X[NC/2]),
-// slot k = 2 X[k]):
-//   pair p (0 .. NC/8): k = 2 p + t ->  oa[p] = slot k,  ob[p] = slot NC/2 - k,
-//   except (t, p) = (0, 0):             oa[0] = slot 0,  ob[0] = slot NC/4.
-// With E / O the half-length spectra of the even / odd samples and w = exp(-2 pi i / NC):
-//   X[k] = E[k] + w^k O[k],  X[NC/2 - k] = conj(E[k] - w^k O[k]).
-template <int NC>
-__device__ __forceinline__ void split_forward(const double (&xs)[NC / 2], const int t,
-                                              double2 (&oa)[NC / 8], double2 (&ob)[NC / 8]) {
-    constexpr int Q = NC / 4, NP = NC / 8;
-    double hr[Q], hi[Q];
-    rtfft::Real<NC / 2>::forward(xs, hr, hi);
-#pragma unroll
-    for (int p = 0; p < NP; ++p) {
-        // lane t = 0 (even samples, E) sends E[2p+1]; lane t = 1 (O) sends O[2p]
-        const double sr = t ? hr[2 * p] : hr[2 * p + 1];
-        const double si = t ? hi[2 * p] : hi[2 * p + 1];
-        const double rr = __shfl_xor_sync(0xffffffffu, sr, 16);
-        const double ri = __shfl_xor_sync(0xffffffffu, si, 16);
-        // generic combination at k = 2p + t
-        const double er = t ? rr : hr[2 * p], ei = t ? ri : hi[2 * p];
-        const double orr = t ? hr[2 * p + 1] : rr, oi = t ? hi[2 * p + 1] : ri;
-        const double c = t ? c_fft_cos[(2 * p + 1) * (64 / NC)] : c_fft_cos[(2 * p) * (64 / NC)];
-        const double s = t ? c_fft_sin[(2 * p + 1) * (64 / NC)] : c_fft_sin[(2 * p) * (64 / NC)];
-        const double wr = fma(c, orr, s * oi), wi = fma(c, oi, -(s * orr));
-        double2 a = make_double2(er + wr, ei + wi);
-        double2 b = make_double2(er - wr, wi - ei);
-        if (p == 0) {
-            // t = 0: E = (E[0], E[Q]) and O = (O[0], O[Q]) are the packed real bins
-            const double2 sa = make_double2(hr[0] + rr, hr[0] - rr);
-            const double2 sb = make_double2(2.0 * hi[0], -2.0 * ri);
-            a = t ? a : sa;
-            b = t ? b : sb;
-        }
-        oa[p] = a;
-        ob[p] = b;
-    }
-}
-
-// ---- split real FFT: inverse ------------------------------------------------ //
-// ia / ib: the slots this lane owns (same ownership as split_forward), holding the
-// TRUE spectrum Y.  Output xs[m] = NC * x[2 m + t].
-//   A[k] = Y[k] + conj(Y[NC/2 - k])           -> even samples
-//   B[k] = (Y[k] - conj(Y[NC/2 - k])) w^{-k}  -> odd samples
-template <int NC>
-__device__ __forceinline__ void split_inverse(const double2 (&ia)[NC / 8], const double2 (&ib)[NC / 8],
-                                              const int t, double (&xs)[NC / 2]) {
-    constexpr int Q = NC / 4, NP = NC / 8;
-    double hr[Q], hi[Q];
-#pragma unroll
-    for (int p = 0; p < NP; ++p) {
-        const double2 yk = ia[p], ym = ib[p];
-        double ar = yk.x + ym.x, ai = yk.y - ym.y;
-        const double dr = yk.x - ym.x, di = yk.y + ym.y;
-        const double c = t ? c_fft_cos[(2 * p + 1) * (64 / NC)] : c_fft_cos[(2 * p) * (64 / NC)];
-        const double s = t ? c_fft_sin[(2 * p + 1) * (64 / NC)] : c_fft_sin[(2 * p) * (64 / NC)];
-        double br = fma(dr, c, -(di * s)), bi = fma(dr, s, di * c);
-        if (p == 0) {
-            // t = 0: yk = (Y[0], Y[NC/2]), ym = Y[NC/4]
-            const double a0 = yk.x + yk.y, aq = 2.0 * ym.x;
-            const double b0 = yk.x - yk.y, bq = -2.0 * ym.y;
-            ar = t ? ar : a0;
-            ai = t ? ai : aq;
-            br = t ? br : b0;
-            bi = t ? bi : bq;
-        }
-        // lane 0 keeps A and sends B[2p]; lane 1 keeps B and sends A[2p+1]
-        const double sr = t ? ar : br, si = t ? ai : bi;
-        const double rr = __shfl_xor_sync(0xffffffffu, sr, 16);
-        const double ri = __shfl_xor_sync(0xffffffffu, si, 16);
-        hr[2 * p] = t ? rr : ar;
-        hi[2 * p] = t ? ri : ai;
-        hr[2 * p + 1] = t ? br : rr;
-        hi[2 * p + 1] = t ? bi : ri;
-    }
-    rtfft::Real<NC / 2>::inverse(hr, hi, xs);
-}
-
 // ---- streaming terms of one angle, one half of the spatial nodes ------------- //
 // Same arithmetic as stream_theta_circ (apply_circ.cuh) for columns whose faces are all
 // conforming (the host routes columns with mortar faces to k_apply_circ); HALF = 0 owns nodes
@@ -387,250 +307,20 @@ __device__ __noinline__ void stream7(const ColMeta& cm, const int th, const int 
 #undef RT_MINE
 }
 
-// ---- scattering, per column: F (FFT) | M (block product) | I (inverse FFT) --------- //
-// F / I: a warp owns whole spatial nodes (an even split of the NN nodes over the warps,
-//        at most 16 / P each); lanes l and l ^ 16 share one sequence (node, a).
-//        F: U -> spectrum slots in W;  I: slots -> real row W[node][theta], in place
-//        (only the owning warp touches a node's row: __syncwarp is enough).
-// M:     lane = spatial node, the frequency slot k is warp-uniform: the P x P complex
-//        block T[k] is read from shared memory with warp-uniform (broadcast) 16-byte
-//        loads -- no per-lane table registers (a constant-bank table was measured slower:
-//        the uniform loads miss in the constant cache);
-//        each lane reads X[k][0..P) of its node once, forms all P outputs (4 P^2 DFMA)
-//        and writes them back in place.  Warp w takes slots w, w + NWARPS, ...
+// ---- scattering, per column: F (half-length FFTs) | M (block product) | I (inverse FFTs) ---- //
+// F / I: a warp owns whole spatial nodes (an even split of the NN nodes over the work warps,
+//        at most 16 / P each); lanes l and l ^ 16 share one sequence (node, a): one transforms
+//        its even, the other its odd samples.  F: U -> half-spectra in W;  I: -> real row
+//        W[node][theta], in place (only the owning warp touches a node's row: __syncwarp).
+// M:     lane = spatial node, the task k (slots k and NC/2 - k) is warp-uniform: the P x P complex
+//        blocks T[k] are read from shared memory with warp-uniform (broadcast) 16-byte loads -- no
+//        per-lane table registers (a constant-bank table was measured slower).
 template <typename Cfg>
 struct CircTab7 {
     double2 v[Cfg::M * Cfg::P * Cfg::P];       // [k][r][a], see rt/tables.py:circulant_spectrum
 };
 
-template <typename Cfg>
-__device__ __noinline__ void fft_f7(const double* __restrict__ U, double* __restrict__ W,
-                                    const int warp, const int lane) {
-    constexpr int NC = Cfg::NC, P = Cfg::P, H = Cfg::H, NP = NC / 8, SU = Cfg::SU, SW = Cfg::SW;
-    constexpr int NN = Cfg::NN;
-    if (warp >= Cfg::WORK_WARPS) return;                        // warp-uniform
-    const int n0 = (warp * NN) / Cfg::WORK_WARPS;
-    const int nw = ((warp + 1) * NN) / Cfg::WORK_WARPS - n0;
-    if (nw == 0) return;
-    const int t = lane >> 4, sq = lane & 15;
-    const bool seq_on = sq < nw * P;
-    const int dn = seq_on ? sq / P : 0, a = seq_on ? sq - dn * P : 0;
-    const int node = n0 + dn;
-    double xs[H];
-    const double* src = U + node * SU + a + t * P;
-#pragma unroll
-    for (int mm = 0; mm < H; ++mm) xs[mm] = src[2 * mm * P];
-    double2 oa[NP], ob[NP];
-    split_forward<NC>(xs, t, oa, ob);
-    if (seq_on) {
-        double2* const wa = reinterpret_cast<double2*>(W + node * SW) + a + t * P;   // slot 2p + t
-        double2* const wb = reinterpret_cast<double2*>(W + node * SW) + a - t * P;   // slot NC/2 - 2p - t
-#pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            wa[2 * p * P] = oa[p];
-            const int sb = (p == 0 && t == 0) ? (NC / 4) : (NC / 2 - 2 * p);
-            wb[sb * P] = ob[p];
-        }
-    }
-}
-
-// one complex slot: y[r] = sum_q T[k][r][q] u[q], in place
-template <typename Cfg>
-__device__ __forceinline__ void mult7_one(double2* const w2, const double2* __restrict__ tk, const bool on) {
-    constexpr int P = Cfg::P;
-    double2 u[P];
-#pragma unroll
-    for (int q = 0; q < P; ++q) u[q] = w2[q];
-#pragma unroll
-    for (int r = 0; r < P; ++r) {
-        double y0 = tk[r * P].x * u[0].x, y1 = -(tk[r * P].y * u[0].y);
-        double y2 = tk[r * P].x * u[0].y, y3 = tk[r * P].y * u[0].x;
-#pragma unroll
-        for (int q = 1; q < P; ++q) {
-            y0 = fma(tk[r * P + q].x, u[q].x, y0);
-            y1 = fma(-tk[r * P + q].y, u[q].y, y1);
-            y2 = fma(tk[r * P + q].x, u[q].y, y2);
-            y3 = fma(tk[r * P + q].y, u[q].x, y3);
-        }
-        if (on) w2[r] = make_double2(y0 + y1, y2 + y3);
-    }
-}
-
-template <typename Cfg>
-__device__ __noinline__ void mult7(double* __restrict__ W, const double2* __restrict__ Ts, const int warp_u,
-                                   const int lane) {
-    constexpr int P = Cfg::P, NN = Cfg::NN, SW = Cfg::SW, M = Cfg::M, WW = Cfg::WORK_WARPS;
-    static_assert(NN <= 32, "one lane per spatial node");
-    if (warp_u >= WW) return;
-    const bool on = lane < NN;
-    double2* const wn = reinterpret_cast<double2*>(W) + (on ? lane : 0) * (SW / 2);
-    int k = warp_u;
-    if (k == 0) {                    // the two real bins (X[0], X[NC/2]): no cross terms
-        double2* const w2 = wn;
-        double2 u[P];
-#pragma unroll
-        for (int q = 0; q < P; ++q) u[q] = w2[q];
-#pragma unroll
-        for (int r = 0; r < P; ++r) {
-            double yr = Ts[r * P].x * u[0].x, yi = Ts[r * P].y * u[0].y;
-#pragma unroll
-            for (int q = 1; q < P; ++q) {
-                yr = fma(Ts[r * P + q].x, u[q].x, yr);
-                yi = fma(Ts[r * P + q].y, u[q].y, yi);
-            }
-            if (on) w2[r] = make_double2(yr, yi);
-        }
-        k += WW;
-    }
-    // pairs of slots (k, k + WW) interleaved: 8 independent chains per output row
-#pragma unroll 1
-    for (; k + WW < M; k += 2 * WW) {
-        double2* const wa = wn + k * P;
-        double2* const wb = wn + (k + WW) * P;
-        const double2* __restrict__ ta = Ts + k * P * P;
-        const double2* __restrict__ tb = Ts + (k + WW) * P * P;
-        double2 ua[P], ub[P];
-#pragma unroll
-        for (int q = 0; q < P; ++q) {
-            ua[q] = wa[q];
-            ub[q] = wb[q];
-        }
-#pragma unroll
-        for (int r = 0; r < P; ++r) {
-            double a0 = ta[r * P].x * ua[0].x, a1 = -(ta[r * P].y * ua[0].y);
-            double a2 = ta[r * P].x * ua[0].y, a3 = ta[r * P].y * ua[0].x;
-            double b0 = tb[r * P].x * ub[0].x, b1 = -(tb[r * P].y * ub[0].y);
-            double b2 = tb[r * P].x * ub[0].y, b3 = tb[r * P].y * ub[0].x;
-#pragma unroll
-            for (int q = 1; q < P; ++q) {
-                a0 = fma(ta[r * P + q].x, ua[q].x, a0);
-                a1 = fma(-ta[r * P + q].y, ua[q].y, a1);
-                a2 = fma(ta[r * P + q].x, ua[q].y, a2);
-                a3 = fma(ta[r * P + q].y, ua[q].x, a3);
-                b0 = fma(tb[r * P + q].x, ub[q].x, b0);
-                b1 = fma(-tb[r * P + q].y, ub[q].y, b1);
-                b2 = fma(tb[r * P + q].x, ub[q].y, b2);
-                b3 = fma(tb[r * P + q].y, ub[q].x, b3);
-            }
-            if (on) {
-                wa[r] = make_double2(a0 + a1, a2 + a3);
-                wb[r] = make_double2(b0 + b1, b2 + b3);
-            }
-        }
-    }
-    if (k < M) mult7_one<Cfg>(wn + k * P, Ts + k * P * P, on);
-}
-
-// Same product when every block T[k] is Hermitian (scattering kernels that are symmetric
-// in (theta, theta'), e.g. any Phi(|theta - theta'|): G = diag(wt) Phi diag(wt) is then
-// symmetric and its block spectrum Hermitian; checked numerically on the host).  Only the
-// upper triangle is read: T[r][q] feeds y[r] += T[r][q] u[q] and y[q] += conj(T[r][q]) u[r],
-// 15 instead of 25 broadcast loads per slot, all P outputs accumulated at once (4 P
-// independent chains, so slots are not paired).
-template <typename Cfg>
-__device__ __noinline__ void mult7_herm(double* __restrict__ W, const double2* __restrict__ Ts,
-                                        const int warp_u, const int lane) {
-    constexpr int P = Cfg::P, NN = Cfg::NN, SW = Cfg::SW, M = Cfg::M, WW = Cfg::WORK_WARPS;
-    static_assert(NN <= 32, "one lane per spatial node");
-    if (warp_u >= WW) return;
-    const bool on = lane < NN;
-    double2* const wn = reinterpret_cast<double2*>(W) + (on ? lane : 0) * (SW / 2);
-#pragma unroll 1
-    for (int k = warp_u; k < M; k += WW) {
-        double2* const w2 = wn + k * P;
-        const double2* __restrict__ tk = Ts + k * P * P;
-        double2 u[P];
-#pragma unroll
-        for (int q = 0; q < P; ++q) u[q] = w2[q];
-        if (k == 0) {            // two real symmetric products: re <- T.x u.x, im <- T.y u.y
-            double yr[P], yi[P];
-#pragma unroll
-            for (int r = 0; r < P; ++r) {
-                const double2 t = tk[r * P + r];
-                yr[r] = t.x * u[r].x;
-                yi[r] = t.y * u[r].y;
-            }
-#pragma unroll
-            for (int r = 0; r < P; ++r)
-#pragma unroll
-                for (int q = r + 1; q < P; ++q) {
-                    const double2 t = tk[r * P + q];
-                    yr[r] = fma(t.x, u[q].x, yr[r]);
-                    yi[r] = fma(t.y, u[q].y, yi[r]);
-                    yr[q] = fma(t.x, u[r].x, yr[q]);
-                    yi[q] = fma(t.y, u[r].y, yi[q]);
-                }
-            if (on) {
-#pragma unroll
-                for (int r = 0; r < P; ++r) w2[r] = make_double2(yr[r], yi[r]);
-            }
-        } else {
-            double y0[P], y1[P], y2[P], y3[P];       // re = y0 - y1, im = y2 + y3
-#pragma unroll
-            for (int r = 0; r < P; ++r) {
-                const double2 t = tk[r * P + r];
-                y0[r] = t.x * u[r].x;
-                y1[r] = t.y * u[r].y;
-                y2[r] = t.x * u[r].y;
-                y3[r] = t.y * u[r].x;
-            }
-#pragma unroll
-            for (int r = 0; r < P; ++r)
-#pragma unroll
-                for (int q = r + 1; q < P; ++q) {
-                    const double2 t = tk[r * P + q];
-                    // y[r] += t u[q]
-                    y0[r] = fma(t.x, u[q].x, y0[r]);
-                    y1[r] = fma(t.y, u[q].y, y1[r]);
-                    y2[r] = fma(t.x, u[q].y, y2[r]);
-                    y3[r] = fma(t.y, u[q].x, y3[r]);
-                    // y[q] += conj(t) u[r]
-                    y0[q] = fma(t.x, u[r].x, y0[q]);
-                    y1[q] = fma(-t.y, u[r].y, y1[q]);
-                    y2[q] = fma(t.x, u[r].y, y2[q]);
-                    y3[q] = fma(-t.y, u[r].x, y3[q]);
-                }
-            if (on) {
-#pragma unroll
-                for (int r = 0; r < P; ++r) w2[r] = make_double2(y0[r] - y1[r], y2[r] + y3[r]);
-            }
-        }
-    }
-}
-
-template <typename Cfg>
-__device__ __noinline__ void fft_i7(double* __restrict__ W, const int warp, const int lane) {
-    constexpr int NC = Cfg::NC, P = Cfg::P, H = Cfg::H, NP = NC / 8, SW = Cfg::SW;
-    constexpr int NN = Cfg::NN;
-    if (warp >= Cfg::WORK_WARPS) return;                        // warp-uniform
-    const int n0 = (warp * NN) / Cfg::WORK_WARPS;
-    const int nw = ((warp + 1) * NN) / Cfg::WORK_WARPS - n0;
-    if (nw == 0) return;
-    const int t = lane >> 4, sq = lane & 15;
-    const bool seq_on = sq < nw * P;
-    const int dn = seq_on ? sq / P : 0, a = seq_on ? sq - dn * P : 0;
-    const int node = n0 + dn;
-    const double2* const wa = reinterpret_cast<const double2*>(W + node * SW) + a + t * P;
-    const double2* const wb = reinterpret_cast<const double2*>(W + node * SW) + a - t * P;
-    double2 ia[NP], ib[NP];
-#pragma unroll
-    for (int p = 0; p < NP; ++p) {
-        ia[p] = wa[2 * p * P];
-        const int sb = (p == 0 && t == 0) ? (NC / 4) : (NC / 2 - 2 * p);
-        ib[p] = wb[sb * P];
-    }
-    __syncwarp();
-    double xs[H];
-    split_inverse<NC>(ia, ib, t, xs);
-    if (seq_on) {
-        double* dst = W + n0 * SW + dn * Cfg::SWR + a + t * P;      // real-row layout, see Circ7Cfg::wrow
-#pragma unroll
-        for (int mm = 0; mm < H; ++mm) dst[2 * mm * P] = xs[mm];
-    }
-}
-
-
-// ---- scattering, E/O form (default): no cross-lane exchange at all ------------------ //
+// ---- E/O form of the transforms: no cross-lane exchange at all ----------------------- //
 // The two lanes of a sequence transform the even / the odd samples (length NC/2, as above)
 // and store their HALF-LENGTH spectra E, O as they are; the last radix-2 stage of the
 // forward transform and the first of the inverse move into the block-product phase, whose
@@ -853,9 +543,9 @@ k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int 
               int interior_only, int herm, const double* __restrict__ x, const double* __restrict__ ghost,
               double* __restrict__ y, const __grid_constant__ CircTab7<Circ7Cfg<N, NC, P>> T,
               const int n_free, const unsigned* __restrict__ halo_flag, const unsigned halo_epoch,
-              const int* __restrict__ resume_in, int* __restrict__ resume_out, const int mode) {
+              const int* __restrict__ resume_in, int* __restrict__ resume_out, const int mode,
+              unsigned* __restrict__ sched) {
     using Cfg = Circ7Cfg<N, NC, P>;
-    const bool eo = mode & 1, inner_fast = (mode & 2) != 0;
     constexpr int NN = Cfg::NN, NT = Cfg::NT, NTP = Cfg::NTP;
     constexpr int SU = Cfg::SU, THREADS = Cfg::THREADS;
     extern __shared__ __align__(16) double smem7[];
@@ -867,17 +557,52 @@ k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int 
     __shared__ ColMeta7 s_meta[3];
     __shared__ __align__(8) unsigned long long s_bar[2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int stride = gridDim.x;
+    // DYNAMIC COLUMN SCHEDULE.  Position blockIdx.x of the column list is the block's first column;
+    // every further position is claimed from the counter sched[0] (position = gridDim.x + old
+    // value), two columns ahead of the one being processed -- the depth of the prefetch pipeline.
+    // A block that becomes resident late (the halo exchange's own kernels hold SMs for ~35 us at
+    // the start of a multi-GPU apply) or runs slower simply claims fewer columns; with static
+    // strides it finished that much later and the whole apply with it.  Positions are handed out
+    // in increasing order, so the ghost-reading columns at the end of the list stay last.
+    // sched[1] counts finished blocks: the last one resets the counters for the next launch
+    // (mode bit 3 = first launch of a split apply: the column counter is kept for the second).
+    //
     // Multi-GPU (rt_apply_with_halo): the columns from position n_free on read ghost traces.
     // Launch 1 runs while the exchange is in flight: a block that reaches its first such column
     // before the exchange has published its epoch in *halo_flag does NOT wait (a persistent
-    // grid that spins can keep the exchange's own kernels off the SMs for ever): it notes
-    // where it stopped in resume_out and exits; launch 2, ordered after the exchange, starts
-    // every block at resume_in.  Blocks that find the flag raised simply carry on.
-    int it = resume_in ? resume_in[blockIdx.x] : blockIdx.x;
-    if (it >= ncols) {
-        if (resume_out && threadIdx.x == 0) resume_out[blockIdx.x] = it;
-        return;
+    // grid that spins can keep the exchange's own kernels off the SMs for ever): it notes its
+    // two claimed positions in resume_out and exits; launch 2, ordered after the exchange,
+    // starts every block with them and goes on claiming.  Blocks that find the flag raised
+    // simply carry on.
+    constexpr int NONE = 0x7fffffff;
+    __shared__ int s_pos[3];                                    // positions of the columns in s_meta[]
+    __shared__ int s_halo_ok;                                   // the halo flag has been seen up
+    __shared__ int s_exhausted, s_stopped;                      // a claim came back empty (claimer only) / left with the flag down
+    const bool claimer = tid == (Cfg::NWARPS - 1) * 32;         // lane 0 of the producer warp
+    auto claim = [&]() -> int {
+        const unsigned v = atomicAdd(&sched[0], 1u);
+        const long long p = (long long)gridDim.x + (long long)v;
+        return p < (long long)ncols ? (int)p : NONE;
+    };
+    if (claimer) {
+        // the current and the next column; the one after next is claimed inside the loop.  A resumed
+        // block (launch 2) starts with the two positions it had claimed when it stopped.
+        bool exhausted = false;
+#pragma unroll 1
+        for (int k = 0; k < 2; ++k) {
+            int p = NONE;
+            if (resume_in) p = resume_in[2 * blockIdx.x + k];
+            else if (k == 0) p = (int)blockIdx.x < ncols ? (int)blockIdx.x : NONE;
+            if (p == NONE && !exhausted && (resume_in || k > 0)) {
+                p = claim();
+                exhausted = p == NONE;
+            }
+            s_pos[k] = p;
+        }
+        s_pos[2] = NONE;
+        s_exhausted = exhausted;
+        s_stopped = 0;
+        s_halo_ok = 0;
     }
     __shared__ int s_go;
     __shared__ StreamArgs7 s_args;
@@ -900,9 +625,11 @@ k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int 
         mbar_init(&s_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    if (warp == 0 && lane < 9) load_col_meta7(m, cols[it], s_meta[0], lane);
-    if (warp == Cfg::NWARPS - 1 && lane < 9 && it + stride < ncols)
-        load_col_meta7(m, cols[it + stride], s_meta[1], lane);
+    __syncthreads();                                            // s_pos published
+    if (s_pos[0] < ncols) {
+        if (warp == 0 && lane < 9) load_col_meta7(m, cols[s_pos[0]], s_meta[0], lane);
+        if (warp == 1 && lane < 9 && s_pos[1] < ncols) load_col_meta7(m, cols[s_pos[1]], s_meta[1], lane);
+    }
     __syncthreads();
 
     // One lane issues the bulk copies of a column (NN rows of the slab + the coefficient
@@ -922,16 +649,27 @@ k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int 
                      (unsigned)(sizeof(double) * 2 * NN), &s_bar[buf]);
         }
     };
-    prefetch(0, s_meta[0]);
+    if (s_pos[0] < ncols) prefetch(0, s_meta[0]);
 
     const bool full = terms == RTB200_TERM_ALL;
     const int half = tid >= Cfg::NTW ? 1 : 0;
     const int th = tid - half * Cfg::NTW;
-    int cur = 0, ms = 0;
-    int n_wait = n_free;     // first position that still has to check the halo flag (ncols once it was seen)
-    unsigned phase = 0;      // bit b: parity of the next completion of buffer b
-    for (; it < ncols; it += stride) {
-        if (it >= n_wait) {
+    // Loop state = the iteration count alone (it must live across the out-of-line phase calls):
+    //   U buffer cur = iter & 1, metadata slot ms = iter % 3,
+    //   mbarrier parity of buffer cur = (iter >> 1) & 1 (its (iter >> 1)-th completion)
+    // The count is kept per warp in shared memory and re-read after the phase calls: as a register
+    // it is spilled across them, and the local-memory reload at the end of the streaming phase
+    // queues behind that phase's global stores.
+    __shared__ int s_iter[Cfg::NWARPS];
+    if (lane == 0) s_iter[warp] = 0;
+    __syncwarp();
+    while (true) {
+        const int iter = *reinterpret_cast<volatile int*>(&s_iter[warp]);
+        const int cur = iter & 1, ms = iter % 3;
+        const unsigned par = (unsigned)(iter >> 1) & 1u;
+        const int it = s_pos[ms];
+        if (it >= ncols) break;
+        if (it >= n_free && !s_halo_ok) {
             if (tid == 0) {
                 unsigned seen;
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(halo_flag) : "memory");
@@ -939,51 +677,53 @@ k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int 
             }
             __syncthreads();
             if (!s_go) {
-                mbar_wait(&s_bar[cur], (phase >> cur) & 1u);     // the copy of this column is in flight
+                mbar_wait(&s_bar[cur], par);                     // the copy of this column is in flight
+                if (tid == 0) s_stopped = 1;
                 break;
             }
-            n_wait = ncols;
+            if (tid == 0) s_halo_ok = 1;                         // published by the barrier below
         }
         __syncthreads();     // everybody is done with the previous column (U[cur ^ 1], W are free)
         const int ms1 = ms == 2 ? 0 : ms + 1, ms2 = ms1 == 2 ? 0 : ms1 + 1;
-        if (it + stride < ncols) prefetch(cur ^ 1, s_meta[ms1]);
-        if (warp == Cfg::NWARPS - 1 && lane < 9 && it + 2 * stride < ncols)
-            load_col_meta7(m, cols[it + 2 * stride], s_meta[ms2], lane);
+        const int it1 = s_pos[ms1];
+        if (it1 < ncols) prefetch(cur ^ 1, s_meta[ms1]);
+        if (warp == Cfg::NWARPS - 1) {
+            // slot ms2 held the previous column (everybody left it at the barrier above): the column
+            // after next is claimed now, its metadata has two iterations to arrive
+            int p = NONE;
+            if (claimer && !s_exhausted && it1 < ncols) {
+                p = claim();
+                s_exhausted = p == NONE;
+            }
+            p = __shfl_sync(0xffffffffu, p, 0);
+            if (lane == 0) s_pos[ms2] = p;
+            if (lane < 9 && p < ncols) load_col_meta7(m, cols[p], s_meta[ms2], lane);
+        }
 
-        mbar_wait(&s_bar[cur], (phase >> cur) & 1u);     // U[cur] / coef[cur] landed
-        phase ^= 1u << cur;
+        mbar_wait(&s_bar[cur], par);                     // U[cur] / coef[cur] landed
         const double* U = Ub + cur * Cfg::U_DOUBLES;
         if (terms & RTB200_TERM_SCAT) {
-            if (eo) {            // E/O form: the radix-2 stage across the lane pair lives in the block product
-                // The barriers between F, M and I only concern the work warps: a named barrier keeps
-                // the producer warp (bulk-copy issue, metadata loads from global memory) out of them,
-                // so that nobody waits for its latencies before the streaming phase.
-                fft_f8<Cfg>(U, W, warp, lane);
-                work_sync<Cfg>(warp);
-                if (herm)
-                    mult8<Cfg, true>(W, reinterpret_cast<const double2*>(Ts), __shfl_sync(0xffffffffu, warp, 0), lane);
-                else
-                    mult8<Cfg, false>(W, reinterpret_cast<const double2*>(Ts), __shfl_sync(0xffffffffu, warp, 0), lane);
-                work_sync<Cfg>(warp);
-                fft_i8<Cfg>(W, warp, lane);
-            } else {             // shuffle form (RTB200_CIRC7_EO=0)
-                fft_f7<Cfg>(U, W, warp, lane);
-                __syncthreads();
-                if (herm)
-                    mult7_herm<Cfg>(W, reinterpret_cast<const double2*>(Ts), __shfl_sync(0xffffffffu, warp, 0), lane);
-                else
-                    mult7<Cfg>(W, reinterpret_cast<const double2*>(Ts), __shfl_sync(0xffffffffu, warp, 0), lane);
-                __syncthreads();
-                fft_i7<Cfg>(W, warp, lane);
-            }
+            // The barriers between F, M and I only concern the work warps: a named barrier keeps
+            // the producer warp (bulk-copy issue, metadata loads from global memory) out of them,
+            // so that nobody waits for its latencies before the streaming phase.
+            fft_f8<Cfg>(U, W, warp, lane);
+            work_sync<Cfg>(warp);
+            if (herm)
+                mult8<Cfg, true>(W, reinterpret_cast<const double2*>(Ts), __shfl_sync(0xffffffffu, warp, 0), lane);
+            else
+                mult8<Cfg, false>(W, reinterpret_cast<const double2*>(Ts), __shfl_sync(0xffffffffu, warp, 0), lane);
+            work_sync<Cfg>(warp);
+            fft_i8<Cfg>(W, warp, lane);
             __syncthreads();
         }
 
         // ---- phase S: streaming terms + scattering combine -> y -------------------- //
         {
+            const int iter_s = *reinterpret_cast<volatile int*>(&s_iter[warp]);
+            const int cur = iter_s & 1, ms = iter_s % 3;
             const ColMeta& cm = s_meta[ms].cm;
             if (th < NT && tid < 2 * Cfg::NTW) {
-                if (full && inner_fast && cm.bdry == 0) {
+                if (full && cm.bdry == 0) {
                     // no face on the domain boundary: every inflow face has a neighbour, no row is masked
                     if (half == 0)
                         stream7<N, 0, true, Cfg, true>(cm, th, cur, s_args);
@@ -1005,8 +745,25 @@ k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int 
                 for (int n = 0; n < NN; ++n) yc[(int64_t)n * NTP] = 0.0;
             }
         }
-        cur ^= 1;
-        ms = ms1;
+        __syncwarp();
+        if (lane == 0) s_iter[warp] = *reinterpret_cast<volatile int*>(&s_iter[warp]) + 1;
+        __syncwarp();
     }
-    if (resume_out && tid == 0) resume_out[blockIdx.x] = it;
+    if (tid == 0) {
+        const int ms = s_iter[0] % 3;
+        if (resume_out) {
+#pragma unroll 1
+            for (int k = 0; k < 2; ++k) {
+                const int slot = (ms + k) % 3;
+                resume_out[2 * blockIdx.x + k] = s_stopped ? s_pos[slot] : NONE;
+            }
+        }
+        __threadfence();
+        const unsigned d = atomicAdd(&sched[1], 1u);
+        if (d == gridDim.x - 1) {                                // last block out: counters ready for the next launch
+            sched[1] = 0u;
+            if (!(mode & 8)) sched[0] = 0u;
+            __threadfence();
+        }
+    }
 }

@@ -48,6 +48,7 @@ static void free_tables(rtb200_ctx* ctx) {
     ctx->allocs.clear();
     ctx->halo_flag_dev = nullptr;      // lives in allocs
     ctx->halo_resume_dev = nullptr;
+    ctx->sched_slots.clear();          // the counters live in allocs
     ctx->buckets.clear();
     ctx->coef_dev = nullptr;
     ctx->ghost_dev = nullptr;
@@ -66,6 +67,8 @@ extern "C" void rtb200_destroy(rtb200_ctx* ctx) {
     for (cudaEvent_t e : ctx->ev_join) cudaEventDestroy(e);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_halo) cudaEventDestroy(ctx->ev_halo);
+    if (ctx->ev_packed) cudaEventDestroy(ctx->ev_packed);
+    ctx->ev_packed = nullptr;
     if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
     ctx->ev_halo = nullptr;
     ctx->comm_stream = nullptr;
@@ -186,10 +189,8 @@ extern "C" int rtb200_set_mesh(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
         ctx->use_circ = !(env && env[0] == '1');
         const char* cv = getenv("RTB200_CIRC_VERSION");
         if (cv && cv[0] == '6') ctx->circ_version = 6;
-        const char* eo = getenv("RTB200_CIRC7_EO");
-        ctx->circ_eo = !(eo && eo[0] == '0');
-        const char* inr = getenv("RTB200_CIRC7_INNER");
-        ctx->circ_inner = !(inr && inr[0] == '0');
+        const char* rsv = getenv("RTB200_HALO_SM_RESERVE");
+        if (rsv && rsv[0] >= '0' && rsv[0] <= '9') ctx->halo_sm_reserve = atoi(rsv);
         const char* hs = getenv("RTB200_HP_STREAM");
         ctx->hp_node_stream = hs && strcmp(hs, "node") == 0;
         const char* hk = getenv("RTB200_HP_KERNEL");

@@ -27,6 +27,154 @@
 // preconditioner.  One block per column; transforms shared with k_apply_circ7.
 #pragma once
 
+// ---- shuffle form of the split transforms (full spectrum in the slot layout [k][a]) ---------- //
+// k_apply_circ7 moved the last radix-2 stage into its block product (E/O form, apply_circ7.cuh);
+// this kernel solves one P x P system per slot and keeps the complete transforms: the two lanes
+// (l, l ^ 16) of a sequence exchange NC/4 doubles with shuffles.
+// ---- split real FFT: forward ------------------------------------------------ //
+// xs[m] = x[2 m + t], m < NC/2.  Output: the NC/4 spectrum slots this lane owns, in
+// the slot convention of fft_real.cuh for length NC (slot 0 = (X[0], X[NC/2]),
+// slot k = 2 X[k]):
+//   pair p (0 .. NC/8): k = 2 p + t ->  oa[p] = slot k,  ob[p] = slot NC/2 - k,
+//   except (t, p) = (0, 0):             oa[0] = slot 0,  ob[0] = slot NC/4.
+// With E / O the half-length spectra of the even / odd samples and w = exp(-2 pi i / NC):
+//   X[k] = E[k] + w^k O[k],  X[NC/2 - k] = conj(E[k] - w^k O[k]).
+template <int NC>
+__device__ __forceinline__ void split_forward(const double (&xs)[NC / 2], const int t,
+                                              double2 (&oa)[NC / 8], double2 (&ob)[NC / 8]) {
+    constexpr int Q = NC / 4, NP = NC / 8;
+    double hr[Q], hi[Q];
+    rtfft::Real<NC / 2>::forward(xs, hr, hi);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        // lane t = 0 (even samples, E) sends E[2p+1]; lane t = 1 (O) sends O[2p]
+        const double sr = t ? hr[2 * p] : hr[2 * p + 1];
+        const double si = t ? hi[2 * p] : hi[2 * p + 1];
+        const double rr = __shfl_xor_sync(0xffffffffu, sr, 16);
+        const double ri = __shfl_xor_sync(0xffffffffu, si, 16);
+        // generic combination at k = 2p + t
+        const double er = t ? rr : hr[2 * p], ei = t ? ri : hi[2 * p];
+        const double orr = t ? hr[2 * p + 1] : rr, oi = t ? hi[2 * p + 1] : ri;
+        const double c = t ? c_fft_cos[(2 * p + 1) * (64 / NC)] : c_fft_cos[(2 * p) * (64 / NC)];
+        const double s = t ? c_fft_sin[(2 * p + 1) * (64 / NC)] : c_fft_sin[(2 * p) * (64 / NC)];
+        const double wr = fma(c, orr, s * oi), wi = fma(c, oi, -(s * orr));
+        double2 a = make_double2(er + wr, ei + wi);
+        double2 b = make_double2(er - wr, wi - ei);
+        if (p == 0) {
+            // t = 0: E = (E[0], E[Q]) and O = (O[0], O[Q]) are the packed real bins
+            const double2 sa = make_double2(hr[0] + rr, hr[0] - rr);
+            const double2 sb = make_double2(2.0 * hi[0], -2.0 * ri);
+            a = t ? a : sa;
+            b = t ? b : sb;
+        }
+        oa[p] = a;
+        ob[p] = b;
+    }
+}
+
+// ---- split real FFT: inverse ------------------------------------------------ //
+// ia / ib: the slots this lane owns (same ownership as split_forward), holding the
+// TRUE spectrum Y.  Output xs[m] = NC * x[2 m + t].
+//   A[k] = Y[k] + conj(Y[NC/2 - k])           -> even samples
+//   B[k] = (Y[k] - conj(Y[NC/2 - k])) w^{-k}  -> odd samples
+template <int NC>
+__device__ __forceinline__ void split_inverse(const double2 (&ia)[NC / 8], const double2 (&ib)[NC / 8],
+                                              const int t, double (&xs)[NC / 2]) {
+    constexpr int Q = NC / 4, NP = NC / 8;
+    double hr[Q], hi[Q];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const double2 yk = ia[p], ym = ib[p];
+        double ar = yk.x + ym.x, ai = yk.y - ym.y;
+        const double dr = yk.x - ym.x, di = yk.y + ym.y;
+        const double c = t ? c_fft_cos[(2 * p + 1) * (64 / NC)] : c_fft_cos[(2 * p) * (64 / NC)];
+        const double s = t ? c_fft_sin[(2 * p + 1) * (64 / NC)] : c_fft_sin[(2 * p) * (64 / NC)];
+        double br = fma(dr, c, -(di * s)), bi = fma(dr, s, di * c);
+        if (p == 0) {
+            // t = 0: yk = (Y[0], Y[NC/2]), ym = Y[NC/4]
+            const double a0 = yk.x + yk.y, aq = 2.0 * ym.x;
+            const double b0 = yk.x - yk.y, bq = -2.0 * ym.y;
+            ar = t ? ar : a0;
+            ai = t ? ai : aq;
+            br = t ? br : b0;
+            bi = t ? bi : bq;
+        }
+        // lane 0 keeps A and sends B[2p]; lane 1 keeps B and sends A[2p+1]
+        const double sr = t ? ar : br, si = t ? ai : bi;
+        const double rr = __shfl_xor_sync(0xffffffffu, sr, 16);
+        const double ri = __shfl_xor_sync(0xffffffffu, si, 16);
+        hr[2 * p] = t ? rr : ar;
+        hi[2 * p] = t ? ri : ai;
+        hr[2 * p + 1] = t ? br : rr;
+        hi[2 * p + 1] = t ? bi : ri;
+    }
+    rtfft::Real<NC / 2>::inverse(hr, hi, xs);
+}
+
+template <typename Cfg>
+__device__ __noinline__ void fft_f7(const double* __restrict__ U, double* __restrict__ W,
+                                    const int warp, const int lane) {
+    constexpr int NC = Cfg::NC, P = Cfg::P, H = Cfg::H, NP = NC / 8, SU = Cfg::SU, SW = Cfg::SW;
+    constexpr int NN = Cfg::NN;
+    if (warp >= Cfg::WORK_WARPS) return;                        // warp-uniform
+    const int n0 = (warp * NN) / Cfg::WORK_WARPS;
+    const int nw = ((warp + 1) * NN) / Cfg::WORK_WARPS - n0;
+    if (nw == 0) return;
+    const int t = lane >> 4, sq = lane & 15;
+    const bool seq_on = sq < nw * P;
+    const int dn = seq_on ? sq / P : 0, a = seq_on ? sq - dn * P : 0;
+    const int node = n0 + dn;
+    double xs[H];
+    const double* src = U + node * SU + a + t * P;
+#pragma unroll
+    for (int mm = 0; mm < H; ++mm) xs[mm] = src[2 * mm * P];
+    double2 oa[NP], ob[NP];
+    split_forward<NC>(xs, t, oa, ob);
+    if (seq_on) {
+        double2* const wa = reinterpret_cast<double2*>(W + node * SW) + a + t * P;   // slot 2p + t
+        double2* const wb = reinterpret_cast<double2*>(W + node * SW) + a - t * P;   // slot NC/2 - 2p - t
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            wa[2 * p * P] = oa[p];
+            const int sb = (p == 0 && t == 0) ? (NC / 4) : (NC / 2 - 2 * p);
+            wb[sb * P] = ob[p];
+        }
+    }
+}
+
+template <typename Cfg>
+__device__ __noinline__ void fft_i7(double* __restrict__ W, const int warp, const int lane) {
+    constexpr int NC = Cfg::NC, P = Cfg::P, H = Cfg::H, NP = NC / 8, SW = Cfg::SW;
+    constexpr int NN = Cfg::NN;
+    if (warp >= Cfg::WORK_WARPS) return;                        // warp-uniform
+    const int n0 = (warp * NN) / Cfg::WORK_WARPS;
+    const int nw = ((warp + 1) * NN) / Cfg::WORK_WARPS - n0;
+    if (nw == 0) return;
+    const int t = lane >> 4, sq = lane & 15;
+    const bool seq_on = sq < nw * P;
+    const int dn = seq_on ? sq / P : 0, a = seq_on ? sq - dn * P : 0;
+    const int node = n0 + dn;
+    const double2* const wa = reinterpret_cast<const double2*>(W + node * SW) + a + t * P;
+    const double2* const wb = reinterpret_cast<const double2*>(W + node * SW) + a - t * P;
+    double2 ia[NP], ib[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        ia[p] = wa[2 * p * P];
+        const int sb = (p == 0 && t == 0) ? (NC / 4) : (NC / 2 - 2 * p);
+        ib[p] = wb[sb * P];
+    }
+    __syncwarp();
+    double xs[H];
+    split_inverse<NC>(ia, ib, t, xs);
+    if (seq_on) {
+        double* dst = W + n0 * SW + dn * Cfg::SWR + a + t * P;      // real-row layout, see Circ7Cfg::wrow
+#pragma unroll
+        for (int mm = 0; mm < H; ++mm) dst[2 * mm * P] = xs[mm];
+    }
+}
+
+
+
 template <int P>
 __device__ __forceinline__ void solve_complex(double (&ar)[P][P], double (&ai)[P][P], double (&br)[P],
                                               double (&bi)[P]) {

@@ -2,7 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "rtb200.h"
@@ -88,8 +90,12 @@ struct rtb200_ctx {
     const double* circ_pool_dev = nullptr;
     bool use_circ = true;          // RTB200_DENSE_SCATTERING=1 in the environment disables it
     int circ_version = 7;          // RTB200_CIRC_VERSION=6 selects the one-block-per-column kernel
-    int circ_eo = 1;               // RTB200_CIRC7_EO=0: shuffle form of the split transforms in k_apply_circ7
-    int circ_inner = 1;            // RTB200_CIRC7_INNER=0: no specialised streaming phase for columns off the boundary
+    // k_apply_circ7 column-schedule counters, one pair per (bucket column list, stream): launches on one
+    // stream are ordered, launches of the same bucket on different streams (the two e2e pipelines) must
+    // not share a counter
+    std::map<std::pair<const void*, void*>, unsigned*> sched_slots;
+    cudaEvent_t ev_packed = nullptr;            // comm stream: traces packed, NCCL next (rt_apply_with_halo)
+    int halo_sm_reserve = 0;       // RTB200_HALO_SM_RESERVE: SMs the persistent apply leaves to the halo exchange's kernels
     bool use_hp = true;            // RTB200_HP_KERNEL=old keeps k_apply for every dense column
     bool hp_node_stream = false;   // RTB200_HP_STREAM=node: node-parallel streaming phase of k_apply
     int64_t launches = 0;

@@ -54,6 +54,39 @@ def main():
         op.close()
         dist.destroy_process_group()
         return
+    if case == "uniform8":
+        # uniform mesh with 8 angular cells per column: ONE circulant bucket served by the
+        # persistent kernel k_apply_circ7 (dynamic column schedule, ghost-reading columns last behind
+        # the halo flag).  Applied twice: as is, and with RTB200_HALO_FORCE_RESUME=1 read by the
+        # library at the second apply (every block stops at its first ghost-reading column and the
+        # second launch finishes the pass).
+        from rt_b200 import configs
+        from rt_b200.dg.flatmesh import FlatMesh, MeshArrays
+        prob = configs.two_strong_scatterers([3.0, 2.0])
+        arrays = MeshArrays.uniform([3.0, 2.0], 4, 3, [3, 3, 3])
+        op = RTOperator(FlatMesh(arrays, rank=rank, nranks=world), prob.kappa, prob.sigma, prob.Phi, device=dev)
+        op.comm_init(rank, world)
+        f = op.flat
+        x = np.random.default_rng(5).standard_normal(f.n_dof_global)
+        xl = x[f.dof0:f.dof0 + f.n_dof].copy()
+        y_loc = op.mult(xl)
+        yi_loc = op.mult(xl, interior_only=True)
+        os.environ["RTB200_HALO_FORCE_RESUME"] = "1"
+        y2_loc = op.mult(xl)
+        del os.environ["RTB200_HALO_FORCE_RESUME"]
+        y3_loc = op.mult(xl)
+        parts = [None] * world
+        dist.all_gather_object(parts, (int(f.dof0), y_loc, yi_loc, y2_loc, y3_loc, int(f.n_ghost),
+                                       op.apply_paths()))
+        if rank == 0:
+            parts.sort(key=lambda p: p[0])
+            np.savez(out, y=np.concatenate([p[1] for p in parts]), yi=np.concatenate([p[2] for p in parts]),
+                     y_forced=np.concatenate([p[3] for p in parts]), y_again=np.concatenate([p[4] for p in parts]),
+                     ghosts=np.array([p[5] for p in parts]), paths=np.array([str(p[6]) for p in parts]))
+        dist.barrier()
+        op.close()
+        dist.destroy_process_group()
+        return
     mesh, d, prob = load_golden(case)
     op = RTOperator(mesh, prob.kappa, prob.sigma, prob.Phi, device=dev, rank=rank, nranks=world)
     _log("operator built")

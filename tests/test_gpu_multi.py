@@ -79,3 +79,41 @@ def test_multi_gpu_hp_spec_twin_equals_single_rank(tmp_path):
     assert rel_err(got["y"], op.mult(x)) <= 1e-13
     ref = O.assemble(hp_spec.hp_spec_mesh(state=st), prob.kappa, prob.sigma, prob.Phi)
     assert rel_err(got["y"], ref["A"] @ x) <= 1e-11
+
+
+def test_multi_gpu_persistent_kernel_with_and_without_resume(tmp_path):
+    """Uniform mesh, 8 angular cells: the single-bucket path of rt_apply_with_halo (k_apply_circ7 with
+    the dynamic column schedule, ghost-reading columns last) on N ranks against the same mesh on one
+    rank and against the oracle; the second apply forces every block to stop at its first
+    ghost-reading column (halo flag treated as down), so the resume launch does real work."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 4 if ngpu >= 4 else 2
+    out = str(tmp_path / "out.npz")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(ROOT, "tests", "multi_gpu_worker.py"), "uniform8", out]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    got = np.load(out)
+    from oracle import rt_oracle as O
+    from rt_b200 import configs
+    from rt_b200.dg.flatmesh import FlatMesh, MeshArrays
+    from rt_b200.rt import RTOperator
+    prob = configs.two_strong_scatterers([3.0, 2.0])
+    op = RTOperator(FlatMesh(MeshArrays.uniform([3.0, 2.0], 4, 3, [3, 3, 3])), prob.kappa, prob.sigma, prob.Phi)
+    x = np.random.default_rng(5).standard_normal(op.n)
+    y1 = op.mult(x)
+    assert (got["ghosts"] > 0).all()
+    assert all("k_apply_circ7" in p for p in got["paths"]), got["paths"]
+    assert rel_err(got["y"], y1) <= 1e-13
+    assert np.array_equal(got["y_forced"], got["y"]), "resumed pass differs from the single pass"
+    assert np.array_equal(got["y_again"], got["y"])
+    assert rel_err(got["yi"], op.mult(x, interior_only=True)) <= 1e-13
+    mesh = configs.build_mesh([3.0, 2.0], [False, False], [3, 3, 3], nref_ang=3, nref_spt=4)
+    ref = O.assemble(mesh, prob.kappa, prob.sigma, prob.Phi)
+    assert rel_err(got["y"], ref["A"] @ x) <= 1e-11
