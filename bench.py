@@ -406,6 +406,7 @@ def run_b200(args):
     for _ in range(2):
         step_ns()
     ms_ns = timed(step_ns, max(3, args.steps // 2)) / max(3, args.steps // 2)
+    apply_paths = op.apply_paths()        # again: carries the halo_stops count of the timed applies (N > 1)
 
     hbm_peak, peak_src = measured_peaks()
     achieved = BYTES_PER_DOF * (n_total / world) / (ms_step * 1e-3) / 1e9     # GB/s per GPU

@@ -383,11 +383,10 @@ static int launch_circ(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int int
             int per_sm = 2;                       // persistent grid: every block the SMs can hold
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::THREADS, Cfg::SMEM);
             if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-            // Multi-GPU apply with the halo exchange in flight (n_free < count): the exchange's own
-            // kernels (k_pack, NCCL send / recv) need a few SMs at the same time.  A grid that fills
-            // every SM makes the blocks that do not fit wait for them (~35 us), and with static
-            // column strides the whole apply then ends that much later; leaving ctx->halo_sm_reserve
-            // SMs free costs their share of the throughput instead (RTB200_HALO_SM_RESERVE, default 4).
+            // RTB200_HALO_SM_RESERVE (default 0) launches the overlapped multi-GPU pass on fewer blocks.
+            // It was tried as a way to leave the halo exchange's kernels room next to the persistent
+            // grid and measured useless (0.8725 / 0.8877 / 0.9067 ms for 0 / 4 / 8 SMs at N = 2): the
+            // block scheduler spreads a smaller grid over all SMs, none is left empty.
             const int sms = (n_free < count || resume) ? std::max(1, ctx->sm_count - ctx->halo_sm_reserve) : ctx->sm_count;
             const int grid = std::min(count, std::max(per_sm, 1) * sms);
             // resume: 1 = first launch of a split apply (blocks note where they stopped),
@@ -402,10 +401,10 @@ static int launch_circ(rtb200_ctx* ctx, const Bucket& b, unsigned terms, int int
                 const auto key = std::make_pair((const void*)b.cols_dev, (void*)st);
                 auto itc = ctx->sched_slots.find(key);
                 if (itc == ctx->sched_slots.end()) {
-                    e = cudaMalloc((void**)&sched, 2 * sizeof(unsigned));
+                    e = cudaMalloc((void**)&sched, 4 * sizeof(unsigned));
                     if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaMalloc(schedule counters)");
                     ctx->allocs.push_back(sched);
-                    e = cudaMemset(sched, 0, 2 * sizeof(unsigned));
+                    e = cudaMemset(sched, 0, 4 * sizeof(unsigned));
                     if (e != cudaSuccess) return rt_cuda(ctx, e, "cudaMemset(schedule counters)");
                     ctx->sched_slots[key] = sched;
                 } else {
@@ -826,6 +825,7 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
     // multi-GPU: one circulant bucket -> split its columns into those that read a ghost trace
     // (face_base <= -2) and the rest, for the overlapped halo exchange of rt_apply_with_halo
     ctx->overlap_ready = false;
+    bool single_persistent = false;
     if (m->n_peer > 0 && ctx->buckets.size() == 1 && ctx->buckets[0].circ_nc > 0) {
         Bucket& b = ctx->buckets[0];
         const auto& cols = acc.begin()->second.cols;
@@ -869,13 +869,22 @@ int rt_apply_setup(rtb200_ctx* ctx, const rtb200_flatmesh* m) {
             RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
             if (!ctx->ev_fork) RT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
         }
+        // Default for this case (one circulant bucket = one persistent grid that fills every SM):
+        // exchange FIRST, then one plain launch.  Overlapping does not pay: the exchange's send /
+        // receive kernel cannot become resident next to two of the apply's blocks on an SM, so it
+        // runs only when they leave -- measured on 2 GPUs (profiles/r02_ae_*): half of the blocks
+        // find the halo flag down at their first ghost-reading column (`halo_stops` of
+        // rtb200_apply_path) and the pass costs 0.858 ms against 0.848 ms serial (0.830 without any
+        // exchange); a high-priority communication stream and SMs left free do not change that.
+        // RTB200_HALO_OVERLAP=1 selects the overlapped single pass (dynamic schedule, resume launch).
         const char* env = getenv("RTB200_HALO_OVERLAP");
-        ctx->overlap_ready = !(env && env[0] == '0');
+        ctx->overlap_ready = env && env[0] == '1';
         const char* fenv = getenv("RTB200_HALO_FUSED");
         ctx->halo_fused = !(fenv && fenv[0] == '0');
+        single_persistent = true;
     }
     ctx->overlap_multi = false;
-    if (m->n_peer > 0 && !ctx->overlap_ready) {
+    if (m->n_peer > 0 && !ctx->overlap_ready && !single_persistent) {
         if (!ctx->comm_stream) {
             int prio_lo = 0, prio_hi = 0;
             RT_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -967,8 +976,16 @@ extern "C" int rtb200_apply_path(const rtb200_ctx* ctx, char* buf, int32_t buf_l
     for (const Bucket& b : ctx->buckets) {
         if (b.circ_nc > 0) {
             const bool v7 = b.circ_nc >= 8 && ctx->circ_version >= 7 && b.circ_conforming;
-            snprintf(line, sizeof(line), "%s<%d,%d,%d> columns=%d groups=%d\n",
-                     v7 ? "k_apply_circ7" : "k_apply_circ", b.n, b.circ_nc, b.circ_p, b.count, b.count);
+            // blocks of a multi-GPU apply that found the halo flag down at their first ghost-reading
+            // column so far (they resume in the second launch): 0 when the exchange is overlapped
+            unsigned stops = 0;
+            for (const auto& kv : ctx->sched_slots)
+                if (kv.first.first == (const void*)b.cols_dev) {
+                    unsigned h[4] = {0, 0, 0, 0};
+                    if (cudaMemcpy(h, kv.second, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) stops += h[2];
+                }
+            snprintf(line, sizeof(line), "%s<%d,%d,%d> columns=%d groups=%d halo_stops=%u\n",
+                     v7 ? "k_apply_circ7" : "k_apply_circ", b.n, b.circ_nc, b.circ_p, b.count, b.count, stops);
         } else if (b.hp) {
             snprintf(line, sizeof(line), "k_apply_hp<%d> columns=%d groups=%d smem=%zu\n", b.n, b.count,
                      b.n_groups, b.smem);

@@ -678,7 +678,10 @@ k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int 
             __syncthreads();
             if (!s_go) {
                 mbar_wait(&s_bar[cur], par);                     // the copy of this column is in flight
-                if (tid == 0) s_stopped = 1;
+                if (tid == 0) {
+                    s_stopped = 1;
+                    atomicAdd(&sched[2], 1u);                    // statistics (rtb200_apply_path)
+                }
                 break;
             }
             if (tid == 0) s_halo_ok = 1;                         // published by the barrier below

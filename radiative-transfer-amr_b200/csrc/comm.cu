@@ -133,10 +133,7 @@ extern "C" int rtb200_halo_exchange(rtb200_ctx* ctx, const double* x_slab_dev, v
     if (!api || !ctx->nccl_comm) return rt_fail(ctx, RTB200_ESTATE, "communicator not initialised");
     cudaStream_t st = (cudaStream_t)stream;
     if (ctx->n_send > 0) {
-        // a small grid: the exchange runs next to the persistent apply, which leaves it only
-        // ctx->halo_sm_reserve SMs (8 resident blocks of 256 threads each); 1.6 MB per neighbour at the
-        // benchmark size, far from bandwidth-bound either way
-        int blocks = (int)std::min<int64_t>((ctx->n_send + 255) / 256, (int64_t)std::max(ctx->halo_sm_reserve, 4) * 8);
+        int blocks = (int)std::min<int64_t>((ctx->n_send + 255) / 256, (int64_t)ctx->sm_count * 2);
         k_pack<<<blocks, 256, 0, st>>>(x_slab_dev, ctx->send_src_dev, ctx->send_dev, ctx->n_send);
         ctx->launches++;
         RT_CUDA(ctx, cudaGetLastError());

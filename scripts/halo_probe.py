@@ -47,6 +47,7 @@ def main():
         "apply_all": timeit(lambda: op.apply_slab(x, y, 15, True)),
         "apply_nobc": timeit(lambda: op.apply_slab(x, y, 7, True)),
         "halo_only": timeit(lambda: op.lib.rtb200_halo_exchange(op.ctx, C.c_void_p(x.data_ptr()), st)),
+        "paths": op.apply_paths(),
         "n_send": int(flat.send_src.size), "n_ghost": int(flat.n_ghost), "peers": [int(p) for p in flat.peer_rank],
     }
     out = [None] * world

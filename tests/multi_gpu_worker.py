@@ -56,10 +56,10 @@ def main():
         return
     if case == "uniform8":
         # uniform mesh with 8 angular cells per column: ONE circulant bucket served by the
-        # persistent kernel k_apply_circ7 (dynamic column schedule, ghost-reading columns last behind
-        # the halo flag).  Applied twice: as is, and with RTB200_HALO_FORCE_RESUME=1 read by the
-        # library at the second apply (every block stops at its first ghost-reading column and the
-        # second launch finishes the pass).
+        # persistent kernel k_apply_circ7.  Default: halo exchange, then one pass.  With
+        # RTB200_HALO_OVERLAP=1 (read when the mesh is set): exchange and pass at the same time, the
+        # ghost-reading columns last behind the halo flag; RTB200_HALO_FORCE_RESUME=1 (read per apply)
+        # makes every block stop at its first ghost-reading column, so the resume launch does real work.
         from rt_b200 import configs
         from rt_b200.dg.flatmesh import FlatMesh, MeshArrays
         prob = configs.two_strong_scatterers([3.0, 2.0])
@@ -71,19 +71,25 @@ def main():
         xl = x[f.dof0:f.dof0 + f.n_dof].copy()
         y_loc = op.mult(xl)
         yi_loc = op.mult(xl, interior_only=True)
+        os.environ["RTB200_HALO_OVERLAP"] = "1"
+        op2 = RTOperator(FlatMesh(arrays, rank=rank, nranks=world), prob.kappa, prob.sigma, prob.Phi, device=dev)
+        del os.environ["RTB200_HALO_OVERLAP"]
+        op2.comm_init(rank, world)
+        y3_loc = op2.mult(xl)
         os.environ["RTB200_HALO_FORCE_RESUME"] = "1"
-        y2_loc = op.mult(xl)
+        y2_loc = op2.mult(xl)
         del os.environ["RTB200_HALO_FORCE_RESUME"]
-        y3_loc = op.mult(xl)
+        stops = op2.apply_paths()
         parts = [None] * world
         dist.all_gather_object(parts, (int(f.dof0), y_loc, yi_loc, y2_loc, y3_loc, int(f.n_ghost),
-                                       op.apply_paths()))
+                                       op.apply_paths() + stops))
         if rank == 0:
             parts.sort(key=lambda p: p[0])
             np.savez(out, y=np.concatenate([p[1] for p in parts]), yi=np.concatenate([p[2] for p in parts]),
                      y_forced=np.concatenate([p[3] for p in parts]), y_again=np.concatenate([p[4] for p in parts]),
                      ghosts=np.array([p[5] for p in parts]), paths=np.array([str(p[6]) for p in parts]))
         dist.barrier()
+        op2.close()
         op.close()
         dist.destroy_process_group()
         return

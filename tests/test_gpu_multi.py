@@ -82,10 +82,11 @@ def test_multi_gpu_hp_spec_twin_equals_single_rank(tmp_path):
 
 
 def test_multi_gpu_persistent_kernel_with_and_without_resume(tmp_path):
-    """Uniform mesh, 8 angular cells: the single-bucket path of rt_apply_with_halo (k_apply_circ7 with
-    the dynamic column schedule, ghost-reading columns last) on N ranks against the same mesh on one
-    rank and against the oracle; the second apply forces every block to stop at its first
-    ghost-reading column (halo flag treated as down), so the resume launch does real work."""
+    """Uniform mesh, 8 angular cells: the single-bucket paths of rt_apply_with_halo (k_apply_circ7 with
+    the dynamic column schedule) on N ranks against the same mesh on one rank and against the
+    oracle: exchange-then-pass (default), overlapped pass with the ghost-reading columns last
+    (RTB200_HALO_OVERLAP=1), and the same with every block forced to stop at its first
+    ghost-reading column, so that the resume launch does real work."""
     import torch
     if not torch.cuda.is_available():
         pytest.fail("GPU test selected but no CUDA device is visible")
@@ -111,8 +112,12 @@ def test_multi_gpu_persistent_kernel_with_and_without_resume(tmp_path):
     assert (got["ghosts"] > 0).all()
     assert all("k_apply_circ7" in p for p in got["paths"]), got["paths"]
     assert rel_err(got["y"], y1) <= 1e-13
+    assert np.array_equal(got["y_again"], got["y"]), "overlapped pass differs from exchange-then-pass"
     assert np.array_equal(got["y_forced"], got["y"]), "resumed pass differs from the single pass"
-    assert np.array_equal(got["y_again"], got["y"])
+    # the forced apply made blocks stop at their first ghost-reading column (statistics of the library)
+    import re
+    stops = [int(v) for p in got["paths"] for v in re.findall(r"halo_stops=(\d+)", str(p))]
+    assert stops and max(stops) > 0, got["paths"]
     assert rel_err(got["yi"], op.mult(x, interior_only=True)) <= 1e-13
     mesh = configs.build_mesh([3.0, 2.0], [False, False], [3, 3, 3], nref_ang=3, nref_spt=4)
     ref = O.assemble(mesh, prob.kappa, prob.sigma, prob.Phi)
