@@ -448,15 +448,16 @@ def run_b200(args):
     e2e = None
     if not args.no_e2e:
         # Every step: pinned host x (dof order) -> device, layout conversion, interior mask,
-        # apply, conversion back, device -> pinned host y.  On one GPU consecutive steps run
-        # on two streams with their own device buffers, so the H2D copy of step i + 1
-        # overlaps the D2H copy of step i (PCIe is full duplex); with several ranks the
-        # library's halo buffers are shared between applies, so steps stay on one stream.
-        nslot = 2
+        # apply, conversion back, device -> pinned host y.  Consecutive steps run on three
+        # streams with their own device buffers; the H2D copies are chained with events (one at
+        # a time, each at the full PCIe rate, instead of two sharing it), so the H2D copy of step
+        # i + 1 runs next to the kernels and the D2H copy of step i (PCIe is full duplex).
+        nslot = 3
         # (with several ranks the halo buffers and the communicator of the context serve one
         #  apply at a time: the applies of the two slots are chained with an event, the copies
         #  and layout conversions of one slot still overlap the other slot's)
         last_apply = [None]
+        last_h2d = [None]
         xh = torch.empty(op.n, dtype=torch.float64).pin_memory()
         xh.normal_(generator=torch.Generator().manual_seed(7))
         slots = []
@@ -471,7 +472,11 @@ def run_b200(args):
         def e2e_step(i):
             sl = slots[i % nslot]
             with torch.cuda.stream(sl["st"]):
+                if last_h2d[0] is not None:
+                    sl["st"].wait_event(last_h2d[0])
                 sl["xd"].copy_(xh, non_blocking=True)
+                last_h2d[0] = torch.cuda.Event()
+                last_h2d[0].record(sl["st"])
                 op.to_slab(sl["xd"], sl["xs"])
                 op.mask_slab(sl["xs"], "interior")
                 if world > 1 and last_apply[0] is not None:
@@ -502,8 +507,8 @@ def run_b200(args):
                 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             return float(ms.item())
 
-        e2e_run(2)
-        k = max(4, min(args.steps, 8))
+        e2e_run(3)
+        k = max(6, min(args.steps, 9))
         ms_e2e = e2e_run(k) / k
         # the last result really is on the host and equals the resident-input result
         op.apply_slab(op.mask_slab(op.to_slab(xh.to(dev)), "interior"), y, 15, True)
