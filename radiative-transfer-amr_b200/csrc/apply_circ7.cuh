@@ -93,6 +93,12 @@ struct Circ7Cfg {
         return n0 * SW + (n - n0) * SWR;
     }
     static constexpr int NA = (NN + 1) / 2;                    // nodes [0, NA) -> half 0, rest -> half 1
+    // E/O transforms (k_apply_circ7): the NN * P sequences are packed 16 to a warp across node
+    // boundaries (two lanes each), so the transform phases run on W8 full warps -- 8 at the
+    // benchmark size, two per scheduler, where an even split of whole nodes took 9 (3 : 2 : 2 : 2).
+    static constexpr int NSEQ = NN * P;
+    static constexpr int W8 = (NSEQ + 15) / 16;
+    static_assert(W8 <= NWARPS, "transform warps");
     // resident blocks per SM the register allocation aims at: 2 at the benchmark size (320
     // threads, 96 registers), more for the small blocks of low-order / few-cell columns
     static constexpr int MINB = 640 / THREADS < 2 ? 2 : (640 / THREADS > 8 ? 8 : 640 / THREADS);
@@ -295,7 +301,7 @@ __device__ __noinline__ void stream7(const ColMeta& cm, const int th, const int 
             if (!RT_MINE(i, j)) continue;
             const int n = i * N + j;
             double acc = v[i][j];
-            if (t_sc) acc = fma(-coef_s[NN + n], ws[Cfg::wrow(n)], acc);
+            if (t_sc) acc = fma(-coef_s[NN + n], ws[n * Cfg::SWR], acc);
             bool masked = false;
             if (i == N - 1) masked = masked || m0;
             if (j == N - 1) masked = masked || m1;
@@ -339,15 +345,10 @@ template <typename Cfg>
 __device__ __noinline__ void fft_f8(const double* __restrict__ U, double* __restrict__ W,
                                     const int warp, const int lane) {
     constexpr int NC = Cfg::NC, P = Cfg::P, H = Cfg::H, Q = Cfg::Q, SU = Cfg::SU, SW = Cfg::SW;
-    constexpr int NN = Cfg::NN;
-    if (warp >= Cfg::WORK_WARPS) return;                        // warp-uniform
-    const int n0 = (warp * NN) / Cfg::WORK_WARPS;
-    const int nw = ((warp + 1) * NN) / Cfg::WORK_WARPS - n0;
-    if (nw == 0) return;
-    const int t = lane >> 4, sq = lane & 15;
-    const bool seq_on = sq < nw * P;
-    const int dn = seq_on ? sq / P : 0, a = seq_on ? sq - dn * P : 0;
-    const int node = n0 + dn;
+    if (warp >= Cfg::W8) return;                                // warp-uniform
+    const int t = lane >> 4, seq = warp * 16 + (lane & 15);
+    const bool seq_on = seq < Cfg::NSEQ;
+    const int node = seq_on ? seq / P : 0, a = seq_on ? seq - node * P : 0;
     double xs[H];
     const double* src = U + node * SU + a + t * P;
 #pragma unroll
@@ -443,7 +444,7 @@ template <typename Cfg, bool HERM>
 __device__ __noinline__ void mult8(double* __restrict__ W, const double2* __restrict__ Ts, const int warp_u,
                                    const int lane) {
     constexpr int NC = Cfg::NC, P = Cfg::P, NN = Cfg::NN, SW = Cfg::SW, H = Cfg::H, Q = Cfg::Q;
-    constexpr int WW = Cfg::WORK_WARPS;
+    constexpr int WW = Cfg::W8;
     static_assert(NN <= 32, "one lane per spatial node");
     if (warp_u >= WW) return;
     const bool on = lane < NN;
@@ -497,18 +498,25 @@ __device__ __noinline__ void mult8(double* __restrict__ W, const double2* __rest
     }
 }
 
+// barrier among the transform warps (all warps when the block has no spare warp)
+template <typename Cfg>
+__device__ __forceinline__ void work_sync(const int warp) {
+    if constexpr (Cfg::W8 < Cfg::NWARPS) {
+        if (warp < Cfg::W8) asm volatile("bar.sync 1, %0;\n" ::"n"(Cfg::W8 * 32) : "memory");
+    } else {
+        __syncthreads();
+    }
+}
+
+// Inverse half-length transforms; the real rows W[node * SWR + theta] overwrite the spectra, and a
+// node's sequences may sit in two warps: all loads, barrier among the transform warps, all stores.
 template <typename Cfg>
 __device__ __noinline__ void fft_i8(double* __restrict__ W, const int warp, const int lane) {
     constexpr int NC = Cfg::NC, P = Cfg::P, H = Cfg::H, Q = Cfg::Q, SW = Cfg::SW;
-    constexpr int NN = Cfg::NN;
-    if (warp >= Cfg::WORK_WARPS) return;                        // warp-uniform
-    const int n0 = (warp * NN) / Cfg::WORK_WARPS;
-    const int nw = ((warp + 1) * NN) / Cfg::WORK_WARPS - n0;
-    if (nw == 0) return;
-    const int t = lane >> 4, sq = lane & 15;
-    const bool seq_on = sq < nw * P;
-    const int dn = seq_on ? sq / P : 0, a = seq_on ? sq - dn * P : 0;
-    const int node = n0 + dn;
+    if (warp >= Cfg::W8) return;                                // warp-uniform
+    const int t = lane >> 4, seq = warp * 16 + (lane & 15);
+    const bool seq_on = seq < Cfg::NSEQ;
+    const int node = seq_on ? seq / P : 0, a = seq_on ? seq - node * P : 0;
     const double2* const w = reinterpret_cast<const double2*>(W + node * SW) + t * P + a;
     double hr[Q], hi[Q];
 #pragma unroll
@@ -517,23 +525,13 @@ __device__ __noinline__ void fft_i8(double* __restrict__ W, const int warp, cons
         hr[j] = v.x;
         hi[j] = v.y;
     }
-    __syncwarp();                                               // the real rows overwrite the spectrum
+    work_sync<Cfg>(warp);                                       // every spectrum entry has been read
     double xs[H];
     rtfft::Real<NC / 2>::inverse(hr, hi, xs);
     if (seq_on) {
-        double* dst = W + n0 * SW + dn * Cfg::SWR + a + t * P;      // real-row layout, see Circ7Cfg::wrow
+        double* dst = W + node * Cfg::SWR + a + t * P;              // uniform real-row stride SWR = P (mod 16)
 #pragma unroll
         for (int mm = 0; mm < H; ++mm) dst[2 * mm * P] = xs[mm];
-    }
-}
-
-// barrier among the work warps (all warps when the block has no spare producer warp)
-template <typename Cfg>
-__device__ __forceinline__ void work_sync(const int warp) {
-    if constexpr (Cfg::WORK_WARPS < Cfg::NWARPS) {
-        if (warp < Cfg::WORK_WARPS) asm volatile("bar.sync 1, %0;\n" ::"n"(Cfg::WORK_WARPS * 32) : "memory");
-    } else {
-        __syncthreads();
     }
 }
 
