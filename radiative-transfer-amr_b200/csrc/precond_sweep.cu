@@ -17,8 +17,9 @@
 //     LEVELS of mutually independent elements -- anti-diagonals on a uniform mesh, a general
 //     DAG with hanging nodes; off-rank (ghost) and periodic wrap-around inflow is lagged
 //     (block Jacobi across ranks, which is what PETSc's bjacobi does too);
-//   * one launch per level, one thread block per element, one thread per angle of the
-//     quadrant: rhs = r - (inflow flux of the already computed z of the upwind columns,
+//   * one launch per level over the flat list of its (element, angle) pairs, one thread each
+//     (k_pc_sweep_flat: full warps whatever the angles per quadrant; one block per element for
+//     the generic nx != ny class): rhs = r - (inflow flux of the already computed z of the upwind columns,
 //     through the same spatial / angular mortar tables as the apply), then the local solve
 //     of the (column, angle) diagonal block  A_loc z = rhs,  nx ny unknowns;
 //   * A_loc / wt = diag(mk) + cos(theta) (dy/2) Bx (x) Wy + sin(theta) (dx/2) Wx (x) By  with

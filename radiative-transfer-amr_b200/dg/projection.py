@@ -84,6 +84,13 @@ class Projection:
             xf = push_forward(x0, x1, xb)
             yf = push_forward(y0, y1, yb)
             cells = {}
+            if func is None:
+                # zero projection (what Problem.solve fills with from_vector): no node coordinates needed
+                for cell_key, cell in sorted(col.cells.items()):
+                    assert cell.is_lf
+                    cells[cell_key] = Projection_Cell(cell, np.zeros([nx, ny, cell.ndofs[0] if has_th else 1]))
+                cols[col_key] = Projection_Column(col, cells)
+                continue
             for cell_key, cell in sorted(col.cells.items()):
                 assert cell.is_lf
                 if has_th:
@@ -130,25 +137,25 @@ class Projection:
         for col_key, col in sorted(self.mesh.cols.items()):
             assert col.is_lf
             nx, ny = col.ndofs
-            for cell_key, cell in sorted(col.cells.items()):
+            pcells = self.cols[col_key].cells
+            items = sorted(col.cells.items())
+            ncol = nx * ny * sum(cell.ndofs[0] for _, cell in items)
+            block = np.array(vec[g:g + ncol], dtype=np.float64)      # one copy per column; the cells view it
+            o = 0
+            for cell_key, cell in items:
                 assert cell.is_lf
                 nth = cell.ndofs[0]
                 n = nx * ny * nth
-                self.cols[col_key].cells[cell_key].vals = \
-                    np.array(vec[g:g + n], dtype=np.float64).reshape(nx, ny, nth)
-                g += n
+                pcells[cell_key].vals = block[o:o + n].reshape(nx, ny, nth)
+                o += n
+            g += ncol
         return self
 
     def checksum(self) -> tuple:
         """(sum, sum of squares) of all nodal values: detects a projection whose values were
         edited after its device copy was made (rt_b200.amr.device_solution)."""
-        s1 = s2 = 0.0
-        for _, col in sorted(self.cols.items()):
-            for _, cell in sorted(col.cells.items()):
-                v = np.asarray(cell.vals, dtype=np.float64)
-                s1 += float(v.sum())
-                s2 += float(np.vdot(v, v))
-        return (s1, s2)
+        v = self.to_vector()
+        return (float(v.sum()), float(np.vdot(v, v)))
 
     def cell_intg_xy(self, col_key: int, cell_key: int) -> np.ndarray:
         """Spatial integral of one cell per angular node, ``[nth]``

@@ -42,12 +42,64 @@ def _eval_nodal(fn, X, Y, Th):
             return np.full((nx, ny, nth), float(out))
     except Exception:
         pass
+    # callables that branch on x / y (the reference's beam boundary condition: ``if (y == y_top)
+    # or (x == x_left)``) still take the whole theta axis at once: nx * ny calls, not nx * ny * nth
     out = np.zeros((nx, ny, nth))
+    try:
+        for i in range(nx):
+            for j in range(ny):
+                row = np.asarray(fn(X[i], Y[j], Th), dtype=np.float64)
+                if row.shape not in ((nth,), ()):
+                    raise ValueError("not a row")
+                out[i, j, :] = row
+        return out
+    except Exception:
+        pass
     for i in range(nx):
         for j in range(ny):
             for a in range(nth):
                 out[i, j, a] = fn(X[i], Y[j], Th[a])
     return out
+
+
+def _column_angles(col):
+    """Angular nodes of all cells of a column side by side (sorted cells), with, per node, the
+    cell factor ``dx dy dth / 8`` of the forcing integral -- up to ``dx dy``, applied by the
+    caller in the reference's order of operations -- and the angular quadrature weight."""
+    x0, y0, x1, y1 = col.pos
+    dx, dy = x1 - x0, y1 - y0
+    cells = [cell for _, cell in sorted(col.cells.items())]
+    nths = [cell.ndofs[0] for cell in cells]
+    th0 = np.array([cell.pos[0] for cell in cells], dtype=np.float64)
+    th1 = np.array([cell.pos[1] for cell in cells], dtype=np.float64)
+    if len(set(nths)) == 1:                  # one order: all cells at once (same arithmetic per entry)
+        _, _, _, _, thb, wth = quad_xyth(nnodes_th=nths[0])
+        th = push_forward(th0.reshape(-1, 1), th1.reshape(-1, 1), np.asarray(thb).reshape(1, -1))
+        fac = np.repeat(dx * dy * (th1 - th0) / 8., nths[0])
+        wt = np.tile(np.asarray(wth, dtype=np.float64), len(cells))
+        return th.reshape(-1), fac, wt, nths
+    th, fac, wt = [], [], []
+    for k, cell in enumerate(cells):
+        assert cell.is_lf
+        nth = nths[k]
+        _, _, _, _, thb, wth = quad_xyth(nnodes_th=nth)
+        th.append(push_forward(th0[k], th1[k], thb))
+        fac.append(np.full(nth, dx * dy * (th1[k] - th0[k]) / 8.))
+        wt.append(np.asarray(wth, dtype=np.float64))
+    return np.concatenate(th), np.concatenate(fac), np.concatenate(wt), nths
+
+
+def _cell_major(vals, nths):
+    """[nx, ny, all angles of the column] -> dof order: cell after cell, C order of
+    ``vals[i, j, a]`` inside a cell (``to_vector.py:16-42``)."""
+    nx, ny, nt = vals.shape
+    if len(set(nths)) == 1:
+        return np.ascontiguousarray(vals.reshape(nx, ny, len(nths), nths[0]).transpose(2, 0, 1, 3)).reshape(-1)
+    out, o = [], 0
+    for nth in nths:
+        out.append(vals[:, :, o:o + nth].reshape(-1))
+        o += nth
+    return np.concatenate(out)
 
 
 def _rank_size(kwargs):
@@ -170,17 +222,13 @@ class Problem:
             nx, ny = col.ndofs
             xb, wx, yb, wy, _, _ = quad_xyth(nnodes_x=nx, nnodes_y=ny)
             X, Y = push_forward(x0, x1, xb), push_forward(y0, y1, yb)
-            for _, cell in sorted(col.cells.items()):
-                assert cell.is_lf
-                th0, th1 = cell.pos
-                nth = cell.ndofs[0]
-                _, _, _, _, thb, wth = quad_xyth(nnodes_th=nth)
-                Th = push_forward(th0, th1, thb)
-                vals = _eval_nodal(self.f, X, Y, Th)
-                scale = (dx * dy * (th1 - th0) / 8.) * (
-                    np.asarray(wx).reshape(nx, 1, 1) * np.asarray(wy).reshape(1, ny, 1)
-                    * np.asarray(wth).reshape(1, 1, nth))
-                parts.append((scale * vals).reshape(-1))
+            # ONE evaluation of f per column: the angular nodes of all its cells side by side
+            # (the reference evaluates node by node; per-cell calls cost 1.6 s on a 4e6-DoF mesh)
+            Th, A, Wth, nths = _column_angles(col)
+            vals = _eval_nodal(self.f, X, Y, Th)
+            scale = A.reshape(1, 1, -1) * (
+                np.asarray(wx).reshape(nx, 1, 1) * np.asarray(wy).reshape(1, ny, 1) * Wth.reshape(1, 1, -1))
+            parts.append(_cell_major(scale * vals, nths))
         return np.concatenate(parts)
 
     def boundary_conditions_vector(self, mesh, **kwargs) -> np.ndarray:
@@ -196,11 +244,8 @@ class Problem:
             X, Y = push_forward(x0, x1, xb), push_forward(y0, y1, yb)
             cells = sorted(col.cells.items())
             if not any(dirac):
-                for _, cell in cells:
-                    assert cell.is_lf
-                    th0, th1 = cell.pos
-                    _, _, _, _, thb, _ = quad_xyth(nnodes_th=cell.ndofs[0])
-                    parts.append(_eval_nodal(bcs, X, Y, push_forward(th0, th1, thb)).reshape(-1))
+                Th, _, _, nths = _column_angles(col)                 # one evaluation per column
+                parts.append(_cell_major(_eval_nodal(bcs, X, Y, Th), nths))
                 continue
             # Dirac source (boundary_conditions_vector.py:142-196): sample at the source location,
             # weight by the (clipped) cardinal functions there.  The reference writes the cells
