@@ -1,5 +1,5 @@
 """Summarise the ptxas -v logs the Makefile leaves next to the objects
-(radiative-transfer-amr_b200/csrc/*.o.ptxas.log) into profiles/r01_ptxas_summary.txt:
+(radiative-transfer-amr_b200/csrc/*.o.ptxas.log) into profiles/r02_ptxas_summary.txt:
 registers, stack and spill bytes of every entry kernel."""
 import glob
 import os
@@ -16,7 +16,7 @@ for log in sorted(glob.glob(os.path.join(CSRC, "*.o.ptxas.log"))):
         name, stack, st, ld, regs = m.groups()
         rows.append("%-40s regs %3s  stack %5s B  spill st/ld %5s/%5s B  %s"
                     % (tu, regs, stack, st, ld, name[:90]))
-with open(os.path.join(ROOT, "profiles", "r01_ptxas_summary.txt"), "w") as fh:
+with open(os.path.join(ROOT, "profiles", "r02_ptxas_summary.txt"), "w") as fh:
     fh.write("ptxas -v summary (sm_100a), entry kernels only; device functions called through the ABI "
              "are listed in the build logs\n")
     fh.write("\n".join(rows) + "\n")
