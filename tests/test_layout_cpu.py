@@ -165,6 +165,73 @@ def test_block_circulant_tables_reproduce_dense_scattering(nc, p):
     assert T.circulant_blocks(T.scattering_kernel(Phi_bad, theta, wt), nc, p) is None
 
 
+def _half_forward(xs):
+    """rtfft::Real<H>::forward in numpy (fft_real.cuh): slot 0 = (Z[0], Z[H/2]) packed, slot k = 2 Z[k]."""
+    h = len(xs)
+    Z = np.fft.fft(xs)
+    out = np.zeros(h // 2, complex)
+    out[0] = Z[0].real + 1j * Z[h // 2].real
+    out[1:] = 2.0 * Z[1:h // 2]
+    return out
+
+
+def _half_inverse(sl):
+    """rtfft::Real<H>::inverse: true spectrum in the same slot layout -> H * x."""
+    h = 2 * len(sl)
+    Z = np.zeros(h, complex)
+    Z[0], Z[h // 2] = sl[0].real, sl[0].imag
+    Z[1:h // 2] = sl[1:]
+    Z[h // 2 + 1:] = np.conj(sl[1:][::-1])
+    return np.fft.ifft(Z).real * h
+
+
+@pytest.mark.parametrize("nc,p", [(8, 3), (16, 4), (32, 5)])
+def test_even_odd_form_of_the_circulant_product(nc, p):
+    """k_apply_circ7's scattering chain in numpy (apply_circ7.cuh: fft_f8 / mult8 / fft_i8): half-length
+    transforms of the even and the odd samples, block-product task k owning the slots k and nc/2 - k
+    (last radix-2 stage of the forward and first of the inverse transform around the two products, task
+    0 owning the packed real bins 0, nc/2 and the slot nc/4), with the device table of
+    rt/tables.py:circulant_spectrum -- against the dense G."""
+    from rt_b200 import configs
+    from rt_b200.rt import tables as T
+    te = np.linspace(0.0, 2 * np.pi, nc + 1)
+    theta, wt = T.angular_nodes(zip(te[:-1], te[1:], [p] * nc))
+    prob = configs.two_strong_scatterers()
+    G = T.scattering_kernel(prob.Phi, theta, wt)
+    tab = T.circulant_spectrum(T.circulant_blocks(G, nc, p))
+    Tc = tab[..., 0] + 1j * tab[..., 1]
+    H, Q = nc // 2, nc // 4
+    x = np.random.default_rng(4).standard_normal((nc, p))
+    E = np.array([_half_forward(x[0::2, a]) for a in range(p)])      # [a][j]
+    O = np.array([_half_forward(x[1::2, a]) for a in range(p)])
+    A, B = np.zeros_like(E), np.zeros_like(O)
+    for k in range(Q):
+        if k == 0:
+            u0 = (E[:, 0].real + O[:, 0].real) + 1j * (E[:, 0].real - O[:, 0].real)   # (X[0], X[nc/2])
+            uq = 2.0 * E[:, 0].imag - 2.0j * O[:, 0].imag                               # 2 X[nc/4]
+            y0 = tab[0, :, :, 0] @ u0.real + 1j * (tab[0, :, :, 1] @ u0.imag)
+            yq = Tc[Q] @ uq
+            A[:, 0] = (y0.real + y0.imag) + 1j * (2.0 * yq.real)
+            B[:, 0] = (y0.real - y0.imag) + 1j * (-2.0 * yq.imag)
+        else:
+            w = np.exp(-2j * np.pi * k / nc)
+            ua = E[:, k] + w * O[:, k]
+            ub = np.conj(E[:, k] - w * O[:, k])
+            ya, yb = Tc[k] @ ua, Tc[H - k] @ ub
+            A[:, k] = ya + np.conj(yb)
+            B[:, k] = (ya - np.conj(yb)) * np.conj(w)
+    y = np.zeros((nc, p))
+    for a in range(p):
+        y[0::2, a] = _half_inverse(A[a])
+        y[1::2, a] = _half_inverse(B[a])
+    ref = (G @ x.reshape(-1)).reshape(nc, p)
+    assert rel_err(y, ref) <= 1e-13
+    # packing of the transform warps: 16 sequences (node, a) per warp, two lanes each
+    nn = 25
+    seqs = [(w * 16 + s) for w in range((nn * p + 15) // 16) for s in range(16) if w * 16 + s < nn * p]
+    assert sorted((q // p, q % p) for q in seqs) == [(n, a) for n in range(nn) for a in range(p)]
+
+
 def test_limits_are_enforced():
     from rt_b200 import configs
     from rt_b200.dg.flatmesh import FlatMesh, MAX_NXY
