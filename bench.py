@@ -17,12 +17,16 @@ One JSON line is printed by rank 0:
   e2e        the same metric through the reference-facing call
              ``RTOperator.mult(x_host)`` (dof-order HOST vectors: pinned H2D copy,
              layout conversion, apply, conversion back, D2H copy, all timed)
-  roofline   dominant kernel (k_apply) against the measured HBM copy bandwidth,
+  roofline   dominant kernel (k_apply_circ7) against the measured HBM copy bandwidth,
              algorithmic traffic 16 B/DoF (read x once, write y once); the FP64
              bound of the dense angular scattering is reported next to it
   cpu_baseline  the oracle's CPU restatement of the reference path (scipy CSR
              SpMV of the assembled A_ii) on a bounded sample of the workload
-  gmres      restarted-GMRES Arnoldi step timing on the same mesh
+  gmres      restarted-GMRES Arnoldi step timing on the same mesh, time-to-solve with the
+             transport-sweep preconditioner (set-up reported next to it), one sweep alone
+  e2e_solve  ``Problem.solve`` end to end on a host ``Mesh`` (single rank)
+  hp         the same apply record for BASELINE configs[4] at spec (workload c5)
+  checksum   ||y||_2 of the timed apply: identical for every number of GPUs
 
 ``--impl reference`` times the reference's own way of applying the operator on
 the host: the explicitly assembled sparse matrix (assembled by the oracle
