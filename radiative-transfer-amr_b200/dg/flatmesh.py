@@ -503,6 +503,13 @@ class FlatMesh:
         """True when the (sig, sig, F) angular coupling is the pointwise upwind
         weight: every inflow cell couples to the same cell only and its scaled
         E_theta block equals diag(wF) to 1e-14."""
+        cache = self.__dict__.setdefault("_acpl_diag_cache", {})   # the answer depends on (signature, face) only
+        if (si, F) in cache:
+            return cache[(si, F)]
+        cache[(si, F)] = ok = self._acpl_is_diagonal_uncached(sig, si, F, tab, eth_at)
+        return ok
+
+    def _acpl_is_diagonal_uncached(self, sig, si, F, tab, eth_at) -> bool:
         o = int(self.sig_th0[si])
         for c0 in range(len(sig.keys)):
             ent = tab[c0].reshape(-1)
