@@ -4,27 +4,31 @@
 // (columns with a mortar face are routed to k_apply_circ by the host).
 //
 // What changed against k_apply_circ (one block per column, phases in lock step):
-//   * persistent blocks (as many as the SMs hold: 2 per SM at the benchmark size) walk
-//     the column list with a grid stride and PREFETCH the next column's slab +
-//     coefficient samples with bulk asynchronous copies (cp.async.bulk, one per slab
-//     row, completing on an mbarrier) into a second buffer while the current column is
-//     processed: the HBM stream and the FP64 phases overlap by construction;
-//   * twice the threads per column at <= 96 registers: every length-NC real FFT is
-//     split over the two lanes (l, l ^ 16) of a warp -- each transforms the even or
-//     the odd samples (length NC/2, in registers), the last radix-2 stage swaps NC/4
-//     doubles with shuffles -- and the streaming terms of an angle are split over
-//     two threads (first / second half of the spatial nodes);
-//   * a warp owns whole spatial nodes in the FFT phases (the inverse transform writes
-//     its rows in place with only a __syncwarp); the block product runs with one lane
-//     per node and a warp-uniform frequency slot, two slots interleaved;
-//   * the last warp is the producer (bulk copies, column metadata two columns ahead in
-//     a 3-slot ring) and stays out of the FFT / block-product phases;
+//   * persistent blocks (as many as the SMs hold: 2 per SM at the benchmark size) with a DYNAMIC
+//     column schedule: the first column of a block is its index, every further one is claimed from
+//     a global counter two columns ahead of the one in flight, and the next column's slab +
+//     coefficient samples are PREFETCHED with bulk asynchronous copies (cp.async.bulk, one per
+//     slab row, completing on an mbarrier) into a second buffer while the current column is
+//     processed: the HBM stream and the FP64 phases overlap by construction, and a block that
+//     starts late or runs slower simply takes fewer columns;
+//   * scattering as F (half-length real FFTs) | M (block product) | I (inverse FFTs): the two
+//     lanes (l, l ^ 16) of a sequence (node, a) transform its even / its odd samples (length NC/2,
+//     in registers) and store the two half-spectra; the block-product thread (lane = node, task k
+//     warp-uniform) owns the slots k and NC/2 - k together and does the last radix-2 stage of the
+//     forward and the first of the inverse transform around its two products -- no shuffles;
+//     the sequences are packed 16 to a warp across node boundaries (8 transform warps at the
+//     benchmark size, two per scheduler), NC/4 product tasks = one per transform warp;
+//   * F | M | I are separated by a named barrier over the transform warps only; the last warp is
+//     the producer (bulk copies, schedule claims, column metadata two columns ahead in a 3-slot
+//     ring) and meets the block at the two full barriers of a column;
+//   * streaming terms of an angle split over two threads (first / second half of the spatial
+//     nodes), specialised for columns off the domain boundary;
 //   * per-angle tables (weights, wt cos, wt sin, upwind bits) and the block spectrum
 //     are staged in shared memory once per block.
 //
-// Shared memory per block at (N, NC, P) = (5, 32, 5): 2 x 33.2 KB (U) + 34.0 KB (W)
-// + 6.4 KB (block spectrum) + 4.5 KB (angle tables) + 0.8 KB = 112.1 KB -> 2 blocks / SM.
-// Measurements and what bounds the kernel: DESIGN.md 4.1, profiles/r01_v13_summary.md.
+// Shared memory per block at (N, NC, P) = (5, 32, 5): 2 x 32.8 KB (U) + 34.0 KB (W)
+// + 6.4 KB (block spectrum) + 4.5 KB (angle tables) + 0.8 KB = 111.3 KB -> 2 blocks / SM.
+// Measurements and what bounds the kernel: DESIGN.md 4.1, profiles/r02_summary.md.
 #pragma once
 #include <utility>
 
@@ -41,6 +45,8 @@ struct Circ7Cfg {
     // The last warp is the producer (bulk copies of the next column, metadata two columns
     // ahead: long-latency global loads); when the block has a warp to spare it is kept out
     // of the FFT and block-product phases so that nobody waits for it at their barriers.
+    // (WORK_WARPS, NW_MAX, node_warp, wrow: whole-node split of the shuffle-form transforms, still
+    //  used by the node-wise preconditioner k_pc_circ in precond_circ.cuh)
     static constexpr int WORK_WARPS = SC_WARPS < NWARPS ? NWARPS - 1 : NWARPS;
     static constexpr int NW_MAX = (NN + WORK_WARPS - 1) / WORK_WARPS;  // nodes per warp (even split)
     // U row stride: even (rows are 16-byte aligned targets of the bulk copies) and with the
@@ -314,10 +320,10 @@ __device__ __noinline__ void stream7(const ColMeta& cm, const int th, const int 
 }
 
 // ---- scattering, per column: F (half-length FFTs) | M (block product) | I (inverse FFTs) ---- //
-// F / I: a warp owns whole spatial nodes (an even split of the NN nodes over the work warps,
-//        at most 16 / P each); lanes l and l ^ 16 share one sequence (node, a): one transforms
-//        its even, the other its odd samples.  F: U -> half-spectra in W;  I: -> real row
-//        W[node][theta], in place (only the owning warp touches a node's row: __syncwarp).
+// F / I: the NN * P sequences (node, a) are packed 16 to a warp across node boundaries (W8
+//        transform warps); lanes l and l ^ 16 share one sequence: one transforms its even, the
+//        other its odd samples.  F: U -> half-spectra in W;  I: -> real row W[node * SWR + theta],
+//        over the spectra (all loads, barrier among the transform warps, all stores).
 // M:     lane = spatial node, the task k (slots k and NC/2 - k) is warp-uniform: the P x P complex
 //        blocks T[k] are read from shared memory with warp-uniform (broadcast) 16-byte loads -- no
 //        per-lane table registers (a constant-bank table was measured slower).
@@ -337,8 +343,8 @@ struct CircTab7 {
 //     B[k] = (Y[k] - conj(Y[NC/2 - k])) w^{-k}    -> odd samples
 // (w = exp(-2 pi i / NC); task 0 owns the packed real bins: slots 0 and NC/4).  Against the
 // shuffle form (split_forward / split_inverse): no SHFL, no per-lane role selects, the
-// same FP64 work, NC/4 block-product tasks of two slots each -- one round over the
-// work warps at the benchmark size instead of two uneven ones.
+// same FP64 work, NC/4 block-product tasks of two slots each -- one per transform warp at the
+// benchmark size instead of two uneven rounds of single-slot tasks.
 // Spectrum layout per node (double2 units): [(2 j + t) P + a], j < NC/4: entry j of the
 // even (t = 0) / odd (t = 1) half-spectrum of sequence a; entry 0 packs the two real bins.
 template <typename Cfg>
@@ -704,7 +710,7 @@ k_apply_circ7(DevMesh m, const int32_t* __restrict__ cols, const int ncols, int 
         mbar_wait(&s_bar[cur], par);                     // U[cur] / coef[cur] landed
         const double* U = Ub + cur * Cfg::U_DOUBLES;
         if (terms & RTB200_TERM_SCAT) {
-            // The barriers between F, M and I only concern the work warps: a named barrier keeps
+            // The barriers between F, M and I only concern the transform warps: a named barrier keeps
             // the producer warp (bulk-copy issue, metadata loads from global memory) out of them,
             // so that nobody waits for its latencies before the streaming phase.
             fft_f8<Cfg>(U, W, warp, lane);
