@@ -383,7 +383,9 @@ int64_t rtb200_launch_count(const rtb200_ctx* ctx);      /* kernels launched so 
  * NUL terminated, truncated to buf_len.  Returns the number of buckets (< 0: error).  The
  * reference has one code path (PETSc MatMult on the assembled AIJ matrix, src/rt/solve.py:68);
  * here the path depends on the column class, and Problem.solve reports it in
- * matrix_info["apply_paths"]. */
+ * matrix_info["apply_paths"].  Lines of the persistent circulant kernel end with
+ * "halo_stops=<n>": blocks of multi-GPU applies that found the halo flag down at their first
+ * ghost-reading column so far (overlapped pass only, RTB200_HALO_OVERLAP=1; 0 otherwise). */
 int  rtb200_apply_path(const rtb200_ctx* ctx, char* buf, int32_t buf_len);
 
 #ifdef __cplusplus
